@@ -1,0 +1,894 @@
+// Engine + C ABI (include/nhans_b200.h): one context per GPU owning a stream, the pre-packed network
+// (plan.h) and the batch workspace; runs the STFT -> towers -> conditioned residual stack -> iSTFT path
+// of N_HANS___Selective_Noise/apply.py:339-457 for whole batches of utterances with no host round trips
+// between the stages.
+#include "../../include/nhans_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "plan.h"
+
+using namespace nhans;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct GemmLayerDev {
+  __half* w = nullptr;
+  KBlockDev* kb = nullptr;
+  float *bias = nullptr, *ttab = nullptr, *ftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
+  CUtensorMap mapA0, mapA1, mapB;
+};
+
+struct NetDev {
+  NetPlan plan;
+  std::vector<__half*> bufs;
+  std::vector<GemmLayerDev> layers;
+  float *first_w = nullptr, *first_bias = nullptr, *first_ttab = nullptr, *first_ftab = nullptr;
+  float *Pa = nullptr, *Pb = nullptr, *c = nullptr;
+  int *u_frame = nullptr, *u_lo = nullptr, *u_hi = nullptr, *u_utt = nullptr;
+  std::vector<void*> allocs;
+  bool ready = false;
+};
+
+struct ProfRec {
+  int kind;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+
+struct Batch {
+  int U = 0;
+  bool has_a = false;
+  bool staged = false, done = false;
+  std::vector<long long> mix_offs, a_offs, b_offs, frame_offs, out_offs, ctx_frame_offs;
+  long long total_frames = 0, total_out = 0;
+  int max_frames = 0;
+  DBuf mix, a, b, d_mix_offs, d_a_offs, d_b_offs, d_frame_offs, d_out_offs, d_ctx_frame_offs;
+  DBuf peak_mix, peak_a, peak_b;
+  DBuf logmag, phase, den, ctxlm_a, ctxlm_b, emb_a, emb_b, cond, out_i16, out_f32, mixproc;
+};
+
+}  // namespace
+
+struct nhans_ctx {
+  int device = 0, variant = 0;
+  int win_cap = 2048, row_cap = 32;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::string json;
+  EncodeTiledFn encode = nullptr;
+  NetDev main_net, tower;
+  int* err_flag_host = nullptr;     // mapped pinned: written by a kernel that gave up waiting
+  int* err_flag_dev = nullptr;
+  DBuf silent_emb;
+  bool silent_ready = false;
+  Batch batch;
+  DBuf tmp[8];
+  cudaEvent_t events[16] = {};
+  bool profile = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_acc[5][4] = {};
+};
+
+namespace {
+
+int fail(nhans_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(ctx, NHANS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                           std::to_string(__LINE__) + ")");                              \
+  } while (0)
+
+template <class T>
+int upload(nhans_ctx* ctx, NetDev& net, const std::vector<T>& h, T** out) {
+  *out = nullptr;
+  if (h.empty()) return 0;
+  void* p = nullptr;
+  CK(cudaMalloc(&p, h.size() * sizeof(T)));
+  net.allocs.push_back(p);
+  CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+int make_map(nhans_ctx* ctx, CUtensorMap* map, const void* base, long long cols, long long rows, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ctx, NHANS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (cols " +
+                                         std::to_string(cols) + ", rows " + std::to_string(rows) + ")");
+  return 0;
+}
+
+void free_net(NetDev& net) {
+  for (void* p : net.allocs) cudaFree(p);
+  net.allocs.clear();
+  net.bufs.clear();
+  net.layers.clear();
+  net.ready = false;
+}
+
+// Allocates the activation grids (zeroed once: padding positions are never written afterwards), uploads
+// packed weights and epilogue tables, encodes the TMA descriptors.
+int realise_net(nhans_ctx* ctx, NetDev& net) {
+  const NetPlan& P = net.plan;
+  net.bufs.assign(P.bufs.size(), nullptr);
+  for (size_t i = 0; i < P.bufs.size(); ++i) {
+    const Grid& g = P.bufs[i];
+    size_t bytes = (size_t)g.pixels * g.C * sizeof(__half);
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    net.allocs.push_back(p);
+    CK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    net.bufs[i] = reinterpret_cast<__half*>(p);
+  }
+  int rc;
+  if ((rc = upload(ctx, net, P.first.w, &net.first_w))) return rc;
+  if ((rc = upload(ctx, net, P.first.epi.bias, &net.first_bias))) return rc;
+  if ((rc = upload(ctx, net, P.first.epi.ttab, &net.first_ttab))) return rc;
+  if ((rc = upload(ctx, net, P.first.epi.ftab, &net.first_ftab))) return rc;
+  if ((rc = upload(ctx, net, P.cond.Pa, &net.Pa))) return rc;
+  if ((rc = upload(ctx, net, P.cond.Pb, &net.Pb))) return rc;
+  if ((rc = upload(ctx, net, P.cond.c, &net.c))) return rc;
+  net.layers.resize(P.gemm.size());
+  for (size_t i = 0; i < P.gemm.size(); ++i) {
+    const GemmLayer& L = P.gemm[i];
+    GemmLayerDev& D = net.layers[i];
+    {
+      void* p = nullptr;
+      CK(cudaMalloc(&p, L.w.size() * 2));
+      net.allocs.push_back(p);
+      CK(cudaMemcpyAsync(p, L.w.data(), L.w.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+      D.w = reinterpret_cast<__half*>(p);
+    }
+    std::vector<KBlockDev> kb(L.kb.size());
+    for (size_t j = 0; j < kb.size(); ++j) kb[j] = {L.kb[j].row_off, L.kb[j].map, L.kb[j].col};
+    if ((rc = upload(ctx, net, kb, &D.kb))) return rc;
+    if ((rc = upload(ctx, net, L.epi.bias, &D.bias))) return rc;
+    if ((rc = upload(ctx, net, L.epi.ttab, &D.ttab))) return rc;
+    if ((rc = upload(ctx, net, L.epi.ftab, &D.ftab))) return rc;
+    if ((rc = upload(ctx, net, L.epi.res_scale, &D.res_scale))) return rc;
+    if ((rc = upload(ctx, net, L.epi.r1_vec, &D.r1_vec))) return rc;
+    for (int a = 0; a < 2; ++a) {
+      int buf = L.a_buf[a] >= 0 ? L.a_buf[a] : L.a_buf[0];
+      int rowlen = L.a_buf[a] >= 0 ? L.a_rowlen[a] : L.a_rowlen[0];
+      const Grid& g = P.bufs[buf];
+      long long elems = (long long)g.pixels * g.C;
+      if (elems % rowlen) return fail(ctx, NHANS_ERR_STATE, "buffer size not a multiple of the TMA row length");
+      if ((rc = make_map(ctx, a == 0 ? &D.mapA0 : &D.mapA1, net.bufs[buf], rowlen, elems / rowlen, 128))) return rc;
+    }
+    if ((rc = make_map(ctx, &D.mapB, D.w, L.K, L.N, L.BN))) return rc;
+  }
+  const int cap = P.capacity;
+  for (int** p : {&net.u_frame, &net.u_lo, &net.u_hi, &net.u_utt}) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, sizeof(int) * (size_t)cap));
+    net.allocs.push_back(q);
+    *p = reinterpret_cast<int*>(q);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  net.ready = true;
+  return 0;
+}
+
+// ---- profiling -----------------------------------------------------------------------------------
+cudaEvent_t get_event(nhans_ctx* ctx) {
+  if (!ctx->ev_pool.empty()) {
+    cudaEvent_t e = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  nhans_ctx* ctx;
+  bool on;
+  ProfRec r;
+  ProfScope(nhans_ctx* c, int kind, double flops, double bytes) : ctx(c), on(c->profile) {
+    if (!on) return;
+    r.kind = kind; r.flops = flops; r.bytes = bytes;
+    r.a = get_event(c); r.b = get_event(c);
+    cudaEventRecord(r.a, c->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, ctx->stream);
+    ctx->prof.push_back(r);
+  }
+};
+
+void prof_collect(nhans_ctx* ctx) {
+  if (ctx->prof.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      double* a = ctx->prof_acc[r.kind];
+      a[0] += 1; a[1] += ms; a[2] += r.flops; a[3] += r.bytes;
+    }
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+}
+
+// ---- network execution ---------------------------------------------------------------------------
+void fill_out(EpiDev& e, const NetDev& net, const Grid& g) {
+  e.out = g.buf >= 0 ? net.bufs[g.buf] : nullptr;
+  e.out_C = g.C;
+  e.o_mode = g.mode; e.o_sh = g.sh; e.o_sw = g.sw; e.o_oy = g.oy; e.o_ox = g.ox;
+  e.o_Hq = g.Hq; e.o_Wq = g.Wq; e.o_H = g.H; e.o_W = g.W;
+  e.o_plane = g.plane_stride;
+}
+
+EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const float* bias_const, const float* ttab,
+                const float* ftab, const float* res_scale, const float* r1_vec, const float* raw, const float* cond_table,
+                float* out_f32) {
+  EpiDev e;
+  memset(&e, 0, sizeof e);
+  if (E.cond_off >= 0) {
+    e.bias = cond_table + E.cond_off;
+    e.bias_stride = net.plan.cond.n_cols;
+  } else {
+    e.bias = bias_const;
+    e.bias_stride = 0;
+  }
+  e.ttab = ttab; e.ftab = ftab;
+  if (E.res_buf >= 0) {
+    e.res = net.bufs[E.res_buf];
+    e.res_C = net.plan.bufs[E.res_buf].C;
+    e.res_scale = res_scale;
+  }
+  e.r1_vec = r1_vec; e.r1_sh = E.r1_sh; e.r1_sw = E.r1_sw; e.raw_oh = E.raw_oh;
+  e.raw = raw;
+  e.relu = E.relu; e.head = E.head;
+  fill_out(e, net, out);
+  e.out_f32 = out_f32;
+  return e;
+}
+
+// Runs `units` windows / context rows whose unit tables are already filled.
+int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const float* cond_table, float* out_f32) {
+  const NetPlan& P = net.plan;
+  UnitTable ut{net.u_frame, net.u_lo, net.u_hi, net.u_utt};
+  {
+    const DirectLayer& D = P.first;
+    DirectDev d;
+    memset(&d, 0, sizeof d);
+    d.units = units;
+    d.kh = D.kh; d.kw = D.kw; d.sh = D.sh; d.sw = D.sw; d.pt = D.pt; d.pl = D.pl;
+    d.Hin = D.Hin; d.Win = D.Win; d.raw_oh = D.raw_oh; d.Ho = D.Ho; d.Wo = D.Wo; d.N = D.N;
+    d.w = net.first_w;
+    d.units_tab = ut;
+    d.epi = make_epi(net, D.epi, D.out, net.first_bias, net.first_ttab, net.first_ftab, nullptr, nullptr, raw, cond_table, nullptr);
+    ProfScope ps(ctx, 3, 2.0 * D.macs_per_unit * units, 0);
+    CK(launch_direct_conv(ctx->stream, d));
+  }
+  for (size_t i = 0; i < P.gemm.size(); ++i) {
+    const GemmLayer& L = P.gemm[i];
+    const GemmLayerDev& D = net.layers[i];
+    GemmDev g;
+    memset(&g, 0, sizeof g);
+    long long M = (long long)units * L.Hq * L.Wq;
+    if (M > 0x7fffffffLL) return fail(ctx, NHANS_ERR_ARG, "too many rows in one pass");
+    g.M = (int)M; g.N = L.N; g.BN = L.BN; g.num_kb = (int)L.kb.size(); g.kb = D.kb;
+    g.Hq = L.Hq; g.Wq = L.Wq; g.Ho = L.Ho; g.Wo = L.Wo;
+    g.units = ut;
+    g.epi = make_epi(net, L.epi, L.out, D.bias, D.ttab, D.ftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);
+    g.err_flag = ctx->err_flag_dev;
+    ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0);
+    CK(launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, g));
+  }
+  return 0;
+}
+
+// Embedding tower over R context rows of ctx_logmag (device, [R][200][201]) -> emb (device, [R][512]).
+int run_tower(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb) {
+  NetDev& net = ctx->tower;
+  const int cap = net.plan.capacity;
+  for (int r0 = 0; r0 < R; r0 += cap) {
+    const int n = std::min(cap, R - r0);
+    CK(launch_units_rows(ctx->stream, r0, n, kCtxFrames, net.u_frame, net.u_lo, net.u_hi, net.u_utt));
+    int rc = run_net(ctx, net, n, ctx_logmag, nullptr, nullptr);
+    if (rc) return rc;
+    ProfScope ps(ctx, 4, 0, 0);
+    CK(launch_mean_pool(ctx->stream, net.bufs[net.plan.pool_buf], n, net.plan.pool_pixels, 512, emb + (size_t)r0 * 512));
+  }
+  return 0;
+}
+
+// Mask network over all frames (device logmag rows) -> denoised rows.
+int run_masknet(nhans_ctx* ctx, const float* logmag, const long long* d_frame_offs, int U, long long total_frames,
+                const float* cond_table, float* den) {
+  NetDev& net = ctx->main_net;
+  const int cap = net.plan.capacity;
+  if (total_frames > 0x7fffffffLL) return fail(ctx, NHANS_ERR_ARG, "too many frames in one batch");
+  for (long long w0 = 0; w0 < total_frames; w0 += cap) {
+    const int n = (int)std::min<long long>(cap, total_frames - w0);
+    CK(launch_units_main(ctx->stream, d_frame_offs, U, (int)w0, n, net.u_frame, net.u_lo, net.u_hi, net.u_utt));
+    int rc = run_net(ctx, net, n, logmag, cond_table, den + (size_t)w0 * kBins);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int ensure_silent(nhans_ctx* ctx) {
+  if (ctx->silent_ready) return 0;
+  // Silent.wav (SN/apply.py:479-480) is all zeros: log(0 + 1e-5) in every bin of all 200 frames.
+  std::vector<float> row((size_t)kCtxFrames * kBins, logf(1e-5f));
+  CK(ctx->tmp[7].ensure(row.size() * 4));
+  CK(cudaMemcpyAsync(ctx->tmp[7].p, row.data(), row.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->silent_emb.ensure(512 * 4));
+  int rc = run_tower(ctx, ctx->tmp[7].as<float>(), 1, ctx->silent_emb.as<float>());
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->silent_ready = true;
+  return 0;
+}
+
+int check_kernel_flag(nhans_ctx* ctx) {
+  if (ctx->err_flag_host && *ctx->err_flag_host)
+    return fail(ctx, NHANS_ERR_KERNEL, "GEMM pipeline timed out waiting on barrier class " + std::to_string(*ctx->err_flag_host));
+  return 0;
+}
+
+int frames_of(long long n) { return n >= 400 ? (int)(1 + (n - 400) / 160) : 0; }
+
+int to_device_offs(nhans_ctx* ctx, DBuf& d, const std::vector<long long>& h) {
+  CK(d.ensure(h.size() * sizeof(long long)));
+  CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int need_weights(nhans_ctx* ctx) {
+  if (!ctx->main_net.ready || !ctx->tower.ready) return fail(ctx, NHANS_ERR_STATE, "nhans_load_weights has not been called");
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* nhans_last_error(const nhans_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int nhans_create(int device, int variant, int win_capacity, int row_capacity, nhans_ctx** out) {
+  if (!out) return NHANS_ERR_ARG;
+  *out = nullptr;
+  if (variant != 0 && variant != 1) { g_create_error = "variant must be 0 or 1"; return NHANS_ERR_ARG; }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0) {
+    g_create_error = std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return NHANS_ERR_CUDA;
+  }
+  if (device < 0 || device >= n_dev) { g_create_error = "device index out of range"; return NHANS_ERR_ARG; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return NHANS_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return NHANS_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only";
+    return NHANS_ERR_CUDA;
+  }
+  std::unique_ptr<nhans_ctx> c(new nhans_ctx);
+  nhans_ctx* ctx = c.get();
+  ctx->device = device;
+  ctx->variant = variant;
+  if (win_capacity > 0) ctx->win_cap = win_capacity;
+  if (row_capacity > 0) ctx->row_cap = row_capacity;
+  ctx->n_sm = prop.multiProcessorCount;
+  auto bail = [&](const std::string& m) { g_create_error = m; return NHANS_ERR_CUDA; };
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess || !fn)
+    return bail("cuTensorMapEncodeTiled is unavailable");
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if ((e = cudaHostAlloc((void**)&ctx->err_flag_host, sizeof(int), cudaHostAllocMapped)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  *ctx->err_flag_host = 0;
+  if ((e = cudaHostGetDevicePointer((void**)&ctx->err_flag_dev, ctx->err_flag_host, 0)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if ((e = gemm_configure()) != cudaSuccess) return bail(std::string("gemm_configure: ") + cudaGetErrorString(e));
+  if ((e = dsp_init_tables()) != cudaSuccess) return bail(std::string("dsp_init_tables: ") + cudaGetErrorString(e));
+  for (auto& ev : ctx->events) cudaEventCreate(&ev);
+  *out = c.release();
+  return NHANS_OK;
+}
+
+void nhans_destroy(nhans_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_net(ctx->main_net);
+  free_net(ctx->tower);
+  Batch& b = ctx->batch;
+  for (DBuf* d : {&b.mix, &b.a, &b.b, &b.d_mix_offs, &b.d_a_offs, &b.d_b_offs, &b.d_frame_offs, &b.d_out_offs,
+                  &b.d_ctx_frame_offs, &b.peak_mix, &b.peak_a, &b.peak_b, &b.logmag, &b.phase, &b.den, &b.ctxlm_a,
+                  &b.ctxlm_b, &b.emb_a, &b.emb_b, &b.cond, &b.out_i16, &b.out_f32, &b.mixproc, &ctx->silent_emb})
+    d->release();
+  for (auto& t : ctx->tmp) t.release();
+  for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
+  for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& ev : ctx->ev_pool) cudaEventDestroy(ev);
+  if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int nhans_load_weights(nhans_ctx* ctx, const char* const* names, const int64_t* sizes, const float* const* data, int n) {
+  if (!ctx || !names || !sizes || !data || n <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  WeightMap w;
+  for (int i = 0; i < n; ++i) w[names[i]] = std::vector<float>(data[i], data[i] + sizes[i]);
+  free_net(ctx->main_net);
+  free_net(ctx->tower);
+  ctx->silent_ready = false;
+  try {
+    ctx->main_net.plan = build_main_plan(w, ctx->variant, ctx->win_cap);
+    ctx->tower.plan = build_tower_plan(w, ctx->row_cap);
+  } catch (const std::exception& ex) {
+    return fail(ctx, NHANS_ERR_ARG, std::string("weights rejected: ") + ex.what());
+  }
+  int rc;
+  if ((rc = realise_net(ctx, ctx->main_net))) return rc;
+  if ((rc = realise_net(ctx, ctx->tower))) return rc;
+  // the packed host copies are no longer needed
+  for (NetDev* nd : {&ctx->main_net, &ctx->tower})
+    for (auto& L : nd->plan.gemm) std::vector<uint16_t>().swap(L.w);
+  return NHANS_OK;
+}
+
+int nhans_output_offsets(const int64_t* mix_offs, int U, int64_t* out_offs) {
+  if (!mix_offs || !out_offs || U < 0) return NHANS_ERR_ARG;
+  out_offs[0] = 0;
+  for (int u = 0; u < U; ++u) {
+    int T = frames_of(mix_offs[u + 1] - mix_offs[u]);
+    out_offs[u + 1] = out_offs[u] + (T > 0 ? (long long)(T - 1) * 160 + 400 : 0);
+  }
+  return NHANS_OK;
+}
+
+int nhans_normalise(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int U, int trim, float* out, int64_t* out_offs) {
+  if (!ctx || !pcm || !offs || !out || !out_offs || U <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<long long> ho(offs, offs + U + 1), oo(U + 1, 0);
+  for (int u = 0; u < U; ++u) {
+    long long n = ho[u + 1] - ho[u];
+    if (trim && n >= 400) n -= (n - 400) % 160;
+    oo[u + 1] = oo[u] + n;
+  }
+  const long long total = ho[U] - ho[0];
+  CK(ctx->tmp[0].ensure(total * 2 + 2));
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, pcm + ho[0], total * 2, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<long long> rel(U + 1);
+  for (int u = 0; u <= U; ++u) rel[u] = ho[u] - ho[0];
+  int rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[1], rel))) return rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[2], oo))) return rc;
+  CK(ctx->tmp[3].ensure(sizeof(int) * U));
+  CK(ctx->tmp[4].ensure(oo[U] * 4 + 4));
+  CK(launch_peaks(ctx->stream, ctx->tmp[0].as<int16_t>(), ctx->tmp[1].as<long long>(), U, ctx->tmp[3].as<int>()));
+  CK(launch_normalise(ctx->stream, ctx->tmp[0].as<int16_t>(), ctx->tmp[1].as<long long>(), ctx->tmp[2].as<long long>(), U,
+                      ctx->tmp[3].as<int>(), ctx->tmp[4].as<float>()));
+  CK(cudaMemcpyAsync(out, ctx->tmp[4].p, oo[U] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int u = 0; u <= U; ++u) out_offs[u] = oo[u];
+  return NHANS_OK;
+}
+
+int nhans_stft(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int U, float* logmag, float* phase,
+               int64_t* frame_offs, int32_t* peak) {
+  if (!ctx || !pcm || !offs || !frame_offs || U <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<long long> rel(U + 1), fo(U + 1, 0);
+  int max_frames = 0;
+  for (int u = 0; u <= U; ++u) rel[u] = offs[u] - offs[0];
+  for (int u = 0; u < U; ++u) {
+    int T = frames_of(offs[u + 1] - offs[u]);
+    max_frames = std::max(max_frames, T);
+    fo[u + 1] = fo[u] + T;
+  }
+  for (int u = 0; u <= U; ++u) frame_offs[u] = fo[u];
+  if (!logmag && !phase && !peak) return NHANS_OK;
+  const long long total = rel[U];
+  CK(ctx->tmp[0].ensure(total * 2 + 2));
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, pcm + offs[0], total * 2, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[1], rel))) return rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[2], fo))) return rc;
+  CK(ctx->tmp[3].ensure(sizeof(int) * U));
+  const size_t sbytes = (size_t)fo[U] * kBins * 4;
+  CK(ctx->tmp[4].ensure(sbytes + 4));
+  CK(ctx->tmp[5].ensure(sbytes + 4));
+  CK(launch_peaks(ctx->stream, ctx->tmp[0].as<int16_t>(), ctx->tmp[1].as<long long>(), U, ctx->tmp[3].as<int>()));
+  {
+    ProfScope ps(ctx, 1, 0, 2.0 * total + 2.0 * sbytes);
+    CK(launch_stft(ctx->stream, ctx->tmp[0].as<int16_t>(), ctx->tmp[1].as<long long>(), ctx->tmp[2].as<long long>(), U,
+                   ctx->tmp[3].as<int>(), max_frames, fo[U], ctx->tmp[4].as<float>(), ctx->tmp[5].as<float>()));
+  }
+  if (logmag) CK(cudaMemcpyAsync(logmag, ctx->tmp[4].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (phase) CK(cudaMemcpyAsync(phase, ctx->tmp[5].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (peak) CK(cudaMemcpyAsync(peak, ctx->tmp[3].p, sizeof(int) * U, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NHANS_OK;
+}
+
+int nhans_embed(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb) {
+  if (!ctx || !ctx_logmag || !emb || R <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = need_weights(ctx))) return rc;
+  const size_t in_bytes = (size_t)R * kCtxFrames * kBins * 4;
+  CK(ctx->tmp[0].ensure(in_bytes));
+  CK(ctx->tmp[1].ensure((size_t)R * 512 * 4));
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, ctx_logmag, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = run_tower(ctx, ctx->tmp[0].as<float>(), R, ctx->tmp[1].as<float>()))) return rc;
+  CK(cudaMemcpyAsync(emb, ctx->tmp[1].p, (size_t)R * 512 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if ((rc = check_kernel_flag(ctx))) return rc;
+  CK(e);
+  return NHANS_OK;
+}
+
+int nhans_masknet(nhans_ctx* ctx, const float* logmag, const int64_t* frame_offs, int U, const float* emb_a,
+                  const float* emb_b, float* denoised) {
+  if (!ctx || !logmag || !frame_offs || !emb_a || !emb_b || !denoised || U <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = need_weights(ctx))) return rc;
+  std::vector<long long> fo(frame_offs, frame_offs + U + 1);
+  const long long total = fo[U];
+  const size_t sbytes = (size_t)total * kBins * 4;
+  const int n_cols = ctx->main_net.plan.cond.n_cols;
+  CK(ctx->tmp[0].ensure(sbytes + 4));
+  CK(ctx->tmp[1].ensure(sbytes + 4));
+  CK(ctx->tmp[2].ensure((size_t)U * 512 * 4));
+  CK(ctx->tmp[3].ensure((size_t)U * 512 * 4));
+  CK(ctx->tmp[4].ensure((size_t)U * n_cols * 4));
+  if ((rc = to_device_offs(ctx, ctx->tmp[5], fo))) return rc;
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, logmag, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmp[2].p, emb_a, (size_t)U * 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmp[3].p, emb_b, (size_t)U * 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_cond_table(ctx->stream, ctx->tmp[2].as<float>(), 512, ctx->tmp[3].as<float>(), 512, U, ctx->main_net.Pa,
+                       ctx->main_net.Pb, ctx->main_net.c, n_cols, ctx->tmp[4].as<float>()));
+  if ((rc = run_masknet(ctx, ctx->tmp[0].as<float>(), ctx->tmp[5].as<long long>(), U, total, ctx->tmp[4].as<float>(),
+                        ctx->tmp[1].as<float>())))
+    return rc;
+  CK(cudaMemcpyAsync(denoised, ctx->tmp[1].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if ((rc = check_kernel_flag(ctx))) return rc;
+  CK(e);
+  return NHANS_OK;
+}
+
+int nhans_istft(nhans_ctx* ctx, const float* logmag, const float* phase, const int64_t* frame_offs, int U,
+                const int32_t* peak, float* wav_f32, int16_t* wav_i16, int64_t* out_offs) {
+  if (!ctx || !logmag || !phase || !frame_offs || !out_offs || U <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  if (wav_i16 && !peak) return fail(ctx, NHANS_ERR_ARG, "int16 output needs the input peaks");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<long long> fo(frame_offs, frame_offs + U + 1), oo(U + 1, 0);
+  int max_frames = 0;
+  for (int u = 0; u < U; ++u) {
+    int T = (int)(fo[u + 1] - fo[u]);
+    max_frames = std::max(max_frames, T);
+    oo[u + 1] = oo[u] + (T > 0 ? (long long)(T - 1) * 160 + 400 : 0);
+  }
+  for (int u = 0; u <= U; ++u) out_offs[u] = oo[u];
+  if (!wav_f32 && !wav_i16) return NHANS_OK;
+  const size_t sbytes = (size_t)fo[U] * kBins * 4;
+  CK(ctx->tmp[0].ensure(sbytes + 4));
+  CK(ctx->tmp[1].ensure(sbytes + 4));
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, logmag, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmp[1].p, phase, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[2], fo))) return rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[3], oo))) return rc;
+  std::vector<int> pk(U, 0);
+  if (peak) for (int u = 0; u < U; ++u) pk[u] = peak[u];
+  CK(ctx->tmp[4].ensure(sizeof(int) * U));
+  CK(cudaMemcpyAsync(ctx->tmp[4].p, pk.data(), sizeof(int) * U, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->tmp[5].ensure(oo[U] * 4 + 4));
+  CK(ctx->tmp[6].ensure(oo[U] * 2 + 4));
+  {
+    ProfScope ps(ctx, 2, 0, 2.0 * sbytes + (wav_f32 ? 4.0 : 0.0) * oo[U] + (wav_i16 ? 2.0 : 0.0) * oo[U]);
+    CK(launch_istft(ctx->stream, ctx->tmp[0].as<float>(), ctx->tmp[1].as<float>(), ctx->tmp[2].as<long long>(),
+                    ctx->tmp[3].as<long long>(), U, ctx->tmp[4].as<int>(), 0, max_frames, wav_f32 ? ctx->tmp[5].as<float>() : nullptr,
+                    wav_i16 ? ctx->tmp[6].as<int16_t>() : nullptr));
+  }
+  if (wav_f32) CK(cudaMemcpyAsync(wav_f32, ctx->tmp[5].p, oo[U] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (wav_i16) CK(cudaMemcpyAsync(wav_i16, ctx->tmp[6].p, oo[U] * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NHANS_OK;
+}
+
+int nhans_upload(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, int U, const int16_t* ctx_a,
+                 const int64_t* a_offs, const int16_t* ctx_b, const int64_t* b_offs) {
+  if (!ctx || !mix || !mix_offs || !ctx_b || !b_offs || U <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  if (ctx_a && !a_offs) return fail(ctx, NHANS_ERR_ARG, "ctx_a given without offsets");
+  if (!ctx_a && ctx->variant != NHANS_VARIANT_SELECTIVE_NOISE)
+    return fail(ctx, NHANS_ERR_ARG, "the separator needs both context recordings");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = need_weights(ctx))) return rc;
+  Batch& b = ctx->batch;
+  b.staged = false; b.done = false;
+  b.U = U;
+  b.has_a = ctx_a != nullptr;
+  auto rel = [&](const int64_t* o, std::vector<long long>& v) {
+    v.resize(U + 1);
+    for (int u = 0; u <= U; ++u) v[u] = o[u] - o[0];
+  };
+  rel(mix_offs, b.mix_offs);
+  rel(b_offs, b.b_offs);
+  if (b.has_a) rel(a_offs, b.a_offs);
+  b.frame_offs.assign(U + 1, 0);
+  b.out_offs.assign(U + 1, 0);
+  b.ctx_frame_offs.resize(U + 1);
+  b.max_frames = 0;
+  for (int u = 0; u < U; ++u) {
+    const int T = frames_of(b.mix_offs[u + 1] - b.mix_offs[u]);
+    b.max_frames = std::max(b.max_frames, T);
+    b.frame_offs[u + 1] = b.frame_offs[u] + T;
+    b.out_offs[u + 1] = b.out_offs[u] + (T > 0 ? (long long)(T - 1) * 160 + 400 : 0);
+    if (frames_of(b.b_offs[u + 1] - b.b_offs[u]) < kCtxFrames || (b.has_a && frames_of(b.a_offs[u + 1] - b.a_offs[u]) < kCtxFrames))
+      return fail(ctx, NHANS_ERR_CONTEXT_TOO_SHORT,
+                  "context clip of utterance " + std::to_string(u) + " yields fewer than 200 STFT frames (needs >= 32240 samples)");
+  }
+  for (int u = 0; u <= U; ++u) b.ctx_frame_offs[u] = (long long)u * kCtxFrames;
+  b.total_frames = b.frame_offs[U];
+  b.total_out = b.out_offs[U];
+  CK(b.mix.ensure(b.mix_offs[U] * 2 + 2));
+  CK(cudaMemcpyAsync(b.mix.p, mix + mix_offs[0], b.mix_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CK(b.b.ensure(b.b_offs[U] * 2 + 2));
+  CK(cudaMemcpyAsync(b.b.p, ctx_b + b_offs[0], b.b_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
+  if (b.has_a) {
+    CK(b.a.ensure(b.a_offs[U] * 2 + 2));
+    CK(cudaMemcpyAsync(b.a.p, ctx_a + a_offs[0], b.a_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = to_device_offs(ctx, b.d_a_offs, b.a_offs))) return rc;
+  }
+  if ((rc = to_device_offs(ctx, b.d_mix_offs, b.mix_offs))) return rc;
+  if ((rc = to_device_offs(ctx, b.d_b_offs, b.b_offs))) return rc;
+  if ((rc = to_device_offs(ctx, b.d_frame_offs, b.frame_offs))) return rc;
+  if ((rc = to_device_offs(ctx, b.d_out_offs, b.out_offs))) return rc;
+  if ((rc = to_device_offs(ctx, b.d_ctx_frame_offs, b.ctx_frame_offs))) return rc;
+  b.staged = true;
+  return NHANS_OK;
+}
+
+int nhans_run(nhans_ctx* ctx) {
+  if (!ctx) return NHANS_ERR_ARG;
+  Batch& b = ctx->batch;
+  if (!b.staged) return fail(ctx, NHANS_ERR_STATE, "nhans_upload has not staged a batch");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  const int U = b.U;
+  const size_t sbytes = (size_t)b.total_frames * kBins * 4;
+  const size_t cbytes = (size_t)U * kCtxFrames * kBins * 4;
+  const int n_cols = ctx->main_net.plan.cond.n_cols;
+  CK(b.peak_mix.ensure(sizeof(int) * U));
+  CK(b.peak_a.ensure(sizeof(int) * U));
+  CK(b.peak_b.ensure(sizeof(int) * U));
+  CK(b.logmag.ensure(sbytes + 4));
+  CK(b.phase.ensure(sbytes + 4));
+  CK(b.den.ensure(sbytes + 4));
+  CK(b.ctxlm_b.ensure(cbytes));
+  CK(b.emb_b.ensure((size_t)U * 512 * 4));
+  CK(b.cond.ensure((size_t)U * n_cols * 4));
+  CK(b.out_i16.ensure(b.total_out * 2 + 2));
+  CK(b.out_f32.ensure(b.total_out * 4 + 4));
+  CK(b.mixproc.ensure(b.total_out * 4 + 4));
+  if (!b.has_a && (rc = ensure_silent(ctx))) return rc;
+
+  // front end: a2-a4 for the mixture and the first 200 frames of each context (SN/apply.py:359-387)
+  CK(launch_peaks(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), U, b.peak_mix.as<int>()));
+  CK(launch_peaks(ctx->stream, b.b.as<int16_t>(), b.d_b_offs.as<long long>(), U, b.peak_b.as<int>()));
+  {
+    ProfScope ps(ctx, 1, 0, 2.0 * b.mix_offs[U] + 2.0 * sbytes);
+    CK(launch_stft(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), b.d_frame_offs.as<long long>(), U,
+                   b.peak_mix.as<int>(), b.max_frames, b.total_frames, b.logmag.as<float>(), b.phase.as<float>()));
+  }
+  {
+    ProfScope ps(ctx, 4, 0, 0);
+    CK(launch_stft(ctx->stream, b.b.as<int16_t>(), b.d_b_offs.as<long long>(), b.d_ctx_frame_offs.as<long long>(), U,
+                   b.peak_b.as<int>(), kCtxFrames, (long long)U * kCtxFrames, b.ctxlm_b.as<float>(), nullptr));
+  }
+  const float* emb_a = nullptr;
+  int stride_a = 0;
+  if (b.has_a) {
+    CK(b.ctxlm_a.ensure(cbytes));
+    CK(b.emb_a.ensure((size_t)U * 512 * 4));
+    CK(launch_peaks(ctx->stream, b.a.as<int16_t>(), b.d_a_offs.as<long long>(), U, b.peak_a.as<int>()));
+    ProfScope ps(ctx, 4, 0, 0);
+    CK(launch_stft(ctx->stream, b.a.as<int16_t>(), b.d_a_offs.as<long long>(), b.d_ctx_frame_offs.as<long long>(), U,
+                   b.peak_a.as<int>(), kCtxFrames, (long long)U * kCtxFrames, b.ctxlm_a.as<float>(), nullptr));
+  }
+  // embedding towers: once per distinct context clip, not once per window
+  if (b.has_a) {
+    if ((rc = run_tower(ctx, b.ctxlm_a.as<float>(), U, b.emb_a.as<float>()))) return rc;
+    emb_a = b.emb_a.as<float>();
+    stride_a = 512;
+  } else {
+    emb_a = ctx->silent_emb.as<float>();
+  }
+  if ((rc = run_tower(ctx, b.ctxlm_b.as<float>(), U, b.emb_b.as<float>()))) return rc;
+  {
+    ProfScope ps(ctx, 4, 0, 0);
+    CK(launch_cond_table(ctx->stream, emb_a, stride_a, b.emb_b.as<float>(), 512, U, ctx->main_net.Pa, ctx->main_net.Pb,
+                         ctx->main_net.c, n_cols, b.cond.as<float>()));
+  }
+  if ((rc = run_masknet(ctx, b.logmag.as<float>(), b.d_frame_offs.as<long long>(), U, b.total_frames, b.cond.as<float>(),
+                        b.den.as<float>())))
+    return rc;
+  {
+    ProfScope ps(ctx, 2, 0, 2.0 * sbytes + 6.0 * b.total_out);
+    CK(launch_istft(ctx->stream, b.den.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
+                    b.d_out_offs.as<long long>(), U, b.peak_mix.as<int>(), 0, b.max_frames, b.out_f32.as<float>(),
+                    b.out_i16.as<int16_t>()));
+  }
+  b.done = true;
+  return NHANS_OK;
+}
+
+int nhans_download(nhans_ctx* ctx, int16_t* out_i16, float* out_f32, float* mixproc_f32) {
+  if (!ctx) return NHANS_ERR_ARG;
+  Batch& b = ctx->batch;
+  if (!b.done) return fail(ctx, NHANS_ERR_STATE, "nhans_run has not produced a batch");
+  CK(cudaSetDevice(ctx->device));
+  if (mixproc_f32) {
+    // 'mixed_processed.wav' (SN/apply.py:457-458): iSTFT of the window centres, i.e. of the input spectrogram
+    ProfScope ps(ctx, 2, 0, 2.0 * b.total_frames * kBins * 4 + 4.0 * b.total_out);
+    CK(launch_istft(ctx->stream, b.logmag.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
+                    b.d_out_offs.as<long long>(), b.U, b.peak_mix.as<int>(), 0, b.max_frames, b.mixproc.as<float>(), nullptr));
+    CK(cudaMemcpyAsync(mixproc_f32, b.mixproc.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (out_i16) CK(cudaMemcpyAsync(out_i16, b.out_i16.p, b.total_out * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_f32) CK(cudaMemcpyAsync(out_f32, b.out_f32.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return NHANS_OK;
+}
+
+int nhans_enhance_batch(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, int U, const int16_t* ctx_a,
+                        const int64_t* a_offs, const int16_t* ctx_b, const int64_t* b_offs, int16_t* out_i16,
+                        float* out_f32, float* mixproc_f32) {
+  int rc;
+  if ((rc = nhans_upload(ctx, mix, mix_offs, U, ctx_a, a_offs, ctx_b, b_offs))) return rc;
+  if ((rc = nhans_run(ctx))) return rc;
+  return nhans_download(ctx, out_i16, out_f32, mixproc_f32);
+}
+
+int nhans_sync(nhans_ctx* ctx) {
+  if (!ctx) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  int rc;
+  if ((rc = check_kernel_flag(ctx))) return rc;
+  CK(e);
+  return NHANS_OK;
+}
+
+int nhans_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes <= 0) return NHANS_ERR_ARG;
+  return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? NHANS_OK : NHANS_ERR_CUDA;
+}
+void nhans_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int nhans_event_record(nhans_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= 16) return NHANS_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->events[slot], ctx->stream));
+  return NHANS_OK;
+}
+int nhans_event_elapsed_ms(nhans_ctx* ctx, int a, int b, double* ms) {
+  if (!ctx || !ms || a < 0 || a >= 16 || b < 0 || b >= 16) return NHANS_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->events[b]));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, ctx->events[a], ctx->events[b]));
+  *ms = f;
+  return NHANS_OK;
+}
+
+int nhans_profile_enable(nhans_ctx* ctx, int on) {
+  if (!ctx) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  prof_collect(ctx);
+  ctx->profile = on != 0;
+  return NHANS_OK;
+}
+int nhans_profile_get(nhans_ctx* ctx, int kind, double* stats) {
+  if (!ctx || !stats || kind < 0 || kind > 4) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  prof_collect(ctx);
+  for (int i = 0; i < 4; ++i) stats[i] = ctx->prof_acc[kind][i];
+  return NHANS_OK;
+}
+int nhans_profile_reset(nhans_ctx* ctx) {
+  if (!ctx) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  prof_collect(ctx);
+  memset(ctx->prof_acc, 0, sizeof ctx->prof_acc);
+  return NHANS_OK;
+}
+
+const char* nhans_plan_json(nhans_ctx* ctx, int net) {
+  if (!ctx) return "";
+  ctx->json = plan_to_json(net == 0 ? ctx->main_net.plan : ctx->tower.plan);
+  return ctx->json.c_str();
+}
+
+int nhans_debug_read_buffer(nhans_ctx* ctx, int net, int buf, uint16_t* out, int64_t n_elems) {
+  if (!ctx || !out) return NHANS_ERR_ARG;
+  NetDev& nd = net == 0 ? ctx->main_net : ctx->tower;
+  if (!nd.ready || buf < 0 || buf >= (int)nd.bufs.size()) return fail(ctx, NHANS_ERR_ARG, "no such buffer");
+  const Grid& g = nd.plan.bufs[buf];
+  if (n_elems > (long long)g.pixels * g.C) return fail(ctx, NHANS_ERR_ARG, "buffer is smaller than requested");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, nd.bufs[buf], (size_t)n_elems * 2, cudaMemcpyDeviceToHost));
+  return NHANS_OK;
+}
+
+int nhans_device_info(nhans_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes) {
+  if (!ctx) return NHANS_ERR_ARG;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (mem_bytes) *mem_bytes = (int64_t)prop.totalGlobalMem;
+  return NHANS_OK;
+}
+
+}  // extern "C"

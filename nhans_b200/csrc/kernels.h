@@ -1,0 +1,101 @@
+// Device-side parameter blocks and kernel launchers of the engine.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nhans {
+
+// Per-unit (window / context row) lookup: frame row of the unit in the raw fp32 spectrogram, the
+// [lo, hi) frame range of the clip it belongs to (rows outside read as 0.0, SN/apply.py:170-173) and
+// the utterance index selecting the conditioning bias row.
+struct UnitTable {
+  const int* frame;
+  const int* lo;
+  const int* hi;
+  const int* utt;
+};
+
+struct EpiDev {
+  const float* bias;        // [n_utt or 1][bias_stride] (+ column offset already applied)
+  int bias_stride;          // 0: one shared row
+  const float* ttab;        // [Ho][N] or null
+  const float* ftab;        // [Wo][N] or null
+  const __half* res;        // identity residual rows [m][res_C] or null
+  int res_C;
+  const float* res_scale;   // [N]
+  const float* r1_vec;      // [N] or null
+  int r1_sh, r1_sw, raw_oh;
+  const float* raw;         // fp32 spectrogram rows [frame][201]
+  int relu;
+  int head;                 // 1: out_f32[n][201] = acc + bias + raw[frame(n)]
+  // output grid (plan.h Grid)
+  __half* out;
+  int out_C;
+  int o_mode, o_sh, o_sw, o_oy, o_ox, o_Hq, o_Wq, o_H, o_W;
+  long long o_plane;
+  float* out_f32;
+};
+
+struct KBlockDev {
+  int32_t row_off;
+  int16_t map;
+  int16_t col;
+};
+
+struct GemmDev {
+  int M;                    // compute rows = units * Hq * Wq
+  int N, BN;
+  int num_kb;
+  const KBlockDev* kb;
+  int Hq, Wq, Ho, Wo;
+  UnitTable units;
+  EpiDev epi;
+  int* err_flag;
+};
+
+struct DirectDev {
+  int units;
+  int kh, kw, sh, sw, pt, pl;
+  int Hin, Win, raw_oh;
+  int Ho, Wo, N;
+  const float* w;           // [kh*kw][N]
+  UnitTable units_tab;
+  EpiDev epi;
+};
+
+constexpr int kGemmThreads = 192;
+int gemm_smem_bytes(int BN, int* stages_out);
+cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
+cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
+                        const CUtensorMap& mapB, const GemmDev& p);
+cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p);
+
+// bias_utt[u][j] = emb_a[u] . Pa[:, j] + emb_b[u] . Pb[:, j] + c[j]
+// (stride 0 broadcasts one embedding row, e.g. the cached Silent.wav embedding of apply_denoiser)
+cudaError_t launch_cond_table(cudaStream_t s, const float* emb_a, int stride_a, const float* emb_b, int stride_b, int U, const float* Pa,
+                              const float* Pb, const float* c, int n_cols, float* out);
+// emb[n][c] = mean over `pixels` rows of act[n][pixels][C]
+cudaError_t launch_mean_pool(cudaStream_t s, const __half* act, int units, int pixels, int C, float* emb);
+cudaError_t launch_units_main(cudaStream_t s, const long long* frame_offs, int U, int w0, int nwin, int* frame, int* lo,
+                              int* hi, int* utt);
+cudaError_t launch_units_rows(cudaStream_t s, int r0, int n, int rows_per_unit, int* frame, int* lo, int* hi, int* utt);
+
+// ---- DSP ----
+// peak[u] = max |pcm| per clip (int32; abs(-32768) wraps to -32768 like numpy int16, SN/apply.py:150)
+cudaError_t launch_peaks(cudaStream_t s, const int16_t* pcm, const long long* offs, int U, int* peak);
+// normalised float32 samples out[out_offs[u] + i] = f32(f64(pcm) / (peak + 1e-6)), i < out_offs[u+1] - out_offs[u]
+cudaError_t launch_normalise(cudaStream_t s, const int16_t* pcm, const long long* offs, const long long* out_offs, int U,
+                             const int* peak, float* out);
+// frames, window, FFT-400, log(|X| + 1e-5), angle: logmag/phase rows [frame_offs[u] + t][201]
+cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* offs, const long long* frame_offs, int U,
+                        const int* peak, int max_frames_per_clip, long long total_frames, float* logmag, float* phase);
+// exp(logmag) * e^{j phase} -> irfft-400 -> synthesis window -> overlap-add -> f32 / int16 samples
+cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase, const long long* frame_offs,
+                         const long long* out_offs, int U, const int* peak, long long total_blocks_hint,
+                         int max_frames_per_clip, float* out_f32, int16_t* out_i16);
+cudaError_t dsp_init_tables();
+
+}  // namespace nhans

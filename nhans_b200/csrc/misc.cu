@@ -1,0 +1,205 @@
+// CUDA-core kernels around the tensor-core GEMMs: the two Cin = 1 convolutions with the implicit
+// 35-frame window gather, the conditioning-projection table, the tower's global mean pool and the
+// per-unit lookup tables.
+#include "kernels.h"
+
+namespace nhans {
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// resblock1_1_conv1 (main.py:162, Cin = 1, 4x4) and embedding/noise_resblock1_1_conv1 (main.py:104, 8x4,
+// stride 3x2): one thread per output pixel, 64 output channels in registers.  Input row r of unit n is
+// frame units.frame[n] + r + raw_oh of the fp32 log-magnitude array; rows outside the clip and outside
+// [0, Hin) read 0.0, which is the zero padding of pad_1D_for_windowing (SN/apply.py:170-173) and of the
+// 'SAME' convolution at once - the [T, 35, 201] window tensor is never materialised.
+__global__ void __launch_bounds__(128)
+direct_conv64_kernel(const DirectDev p) {
+  extern __shared__ float s_w[];                       // [kh*kw][64]
+  const int taps = p.kh * p.kw;
+  for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) s_w[i] = p.w[i];
+  __syncthreads();
+  const long long total = (long long)p.units * p.Ho * p.Wo;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int unit = (int)(idx / (p.Ho * p.Wo));
+  const int rem = (int)(idx - (long long)unit * p.Ho * p.Wo);
+  const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
+  const int frame0 = p.units_tab.frame[unit] + p.raw_oh;
+  const int lo = p.units_tab.lo[unit], hi = p.units_tab.hi[unit];
+  const EpiDev& e = p.epi;
+
+  float acc[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+  for (int i = 0; i < p.kh; ++i) {
+    const int r = ho * p.sh + i - p.pt;
+    const int frame = frame0 + r;
+    if (r < 0 || r >= p.Hin || frame < lo || frame >= hi) continue;
+    const float* row = e.raw + (size_t)frame * 201;
+    for (int j = 0; j < p.kw; ++j) {
+      const int f = wo * p.sw + j - p.pl;
+      if (f < 0 || f >= p.Win) continue;
+      const float x = row[f];
+      const float4* w4 = reinterpret_cast<const float4*>(s_w + (i * p.kw + j) * 64);
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        const float4 w = w4[n];
+        acc[4 * n] = fmaf(x, w.x, acc[4 * n]);
+        acc[4 * n + 1] = fmaf(x, w.y, acc[4 * n + 1]);
+        acc[4 * n + 2] = fmaf(x, w.z, acc[4 * n + 2]);
+        acc[4 * n + 3] = fmaf(x, w.w, acc[4 * n + 3]);
+      }
+    }
+  }
+  const int utt = p.units_tab.utt ? p.units_tab.utt[unit] : 0;
+  const float4* b4 = reinterpret_cast<const float4*>(e.bias + (size_t)utt * e.bias_stride);
+  const float4* t4 = e.ttab ? reinterpret_cast<const float4*>(e.ttab + (size_t)ho * 64) : nullptr;
+  const float4* f4 = e.ftab ? reinterpret_cast<const float4*>(e.ftab + (size_t)wo * 64) : nullptr;
+  const int y = ho + e.o_oy, x = wo + e.o_ox;
+  const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
+  const long long pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw);
+  uint4* out = reinterpret_cast<uint4*>(e.out + pix * e.out_C);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n4 = 2 * g + h;
+      float4 b = b4[n4];
+      if (t4) { const float4 t = t4[n4]; b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w; }
+      if (f4) { const float4 t = f4[n4]; b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w; }
+      v[4 * h] = acc[4 * n4] + b.x;
+      v[4 * h + 1] = acc[4 * n4 + 1] + b.y;
+      v[4 * h + 2] = acc[4 * n4 + 2] + b.z;
+      v[4 * h + 3] = acc[4 * n4 + 3] + b.w;
+    }
+    if (e.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    uint4 o;
+    o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+    o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+    out[g] = o;
+  }
+}
+
+// bias_utt[u][j] = emb_a[u] . Pa[:, j] + emb_b[u] . Pb[:, j] + c[j]   (all 32 conditioning projections of
+// main.py:142-148 with the batch-norm scale of their site folded in; one small fp32 GEMM per batch)
+constexpr int kCondU = 8;
+__global__ void __launch_bounds__(128)
+cond_table_kernel(const float* __restrict__ emb_a, int stride_a, const float* __restrict__ emb_b, int stride_b, int U, const float* __restrict__ Pa,
+                  const float* __restrict__ Pb, const float* __restrict__ c, int n_cols, float* __restrict__ out) {
+  __shared__ float s_a[kCondU][512];
+  __shared__ float s_b[kCondU][512];
+  const int u0 = blockIdx.y * kCondU;
+  for (int i = threadIdx.x; i < kCondU * 512; i += blockDim.x) {
+    const int uu = i >> 9, k = i & 511;
+    const bool ok = u0 + uu < U;
+    s_a[uu][k] = ok ? emb_a[(size_t)(u0 + uu) * stride_a + k] : 0.f;
+    s_b[uu][k] = ok ? emb_b[(size_t)(u0 + uu) * stride_b + k] : 0.f;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cols) return;
+  float acc[kCondU];
+#pragma unroll
+  for (int uu = 0; uu < kCondU; ++uu) acc[uu] = 0.f;
+  for (int k = 0; k < 512; ++k) {
+    const float pa = Pa[(size_t)k * n_cols + j], pb = Pb[(size_t)k * n_cols + j];
+#pragma unroll
+    for (int uu = 0; uu < kCondU; ++uu) acc[uu] = fmaf(s_a[uu][k], pa, fmaf(s_b[uu][k], pb, acc[uu]));
+  }
+  const float cj = c[j];
+#pragma unroll
+  for (int uu = 0; uu < kCondU; ++uu)
+    if (u0 + uu < U) out[(size_t)(u0 + uu) * n_cols + j] = acc[uu] + cj;
+}
+
+// tf.nn.avg_pool2d over the whole 23 x 26 map (main.py:199-202): emb[n][c] = mean_p act[n][p][c]
+__global__ void mean_pool_kernel(const __half* __restrict__ act, int pixels, int C, float* __restrict__ emb) {
+  const int n = blockIdx.x;
+  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+    float sx = 0.f, sy = 0.f;
+    const __half2* p = reinterpret_cast<const __half2*>(act + (size_t)n * pixels * C) + c2;
+    for (int i = 0; i < pixels; ++i) {
+      const float2 v = __half22float2(p[(size_t)i * (C / 2)]);
+      sx += v.x; sy += v.y;
+    }
+    emb[(size_t)n * C + 2 * c2] = sx / (float)pixels;
+    emb[(size_t)n * C + 2 * c2 + 1] = sy / (float)pixels;
+  }
+}
+
+// Window n of the chunk is global frame w0 + n (one window per STFT frame, SN/apply.py:378); its clip is
+// found by binary search in frame_offs.
+__global__ void units_main_kernel(const long long* __restrict__ frame_offs, int U, int w0, int nwin, int* frame, int* lo,
+                                  int* hi, int* utt) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nwin) return;
+  const long long g = (long long)w0 + n;
+  int a = 0, b = U;                                     // frame_offs[a] <= g < frame_offs[b]
+  while (b - a > 1) {
+    const int mid = (a + b) >> 1;
+    if (frame_offs[mid] <= g) a = mid; else b = mid;
+  }
+  frame[n] = (int)g;
+  lo[n] = (int)frame_offs[a];
+  hi[n] = (int)frame_offs[a + 1];
+  utt[n] = a;
+}
+
+__global__ void units_rows_kernel(int r0, int n_units, int rows, int* frame, int* lo, int* hi, int* utt) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_units) return;
+  frame[n] = (r0 + n) * rows;
+  lo[n] = (r0 + n) * rows;
+  hi[n] = (r0 + n + 1) * rows;
+  utt[n] = 0;
+}
+
+}  // namespace
+
+cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p) {
+  if (p.units <= 0) return cudaSuccess;
+  if (p.N != 64) return cudaErrorInvalidValue;
+  const long long total = (long long)p.units * p.Ho * p.Wo;
+  const int threads = 128;
+  const long long blocks = (total + threads - 1) / threads;
+  direct_conv64_kernel<<<(unsigned)blocks, threads, p.kh * p.kw * 64 * sizeof(float), s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cond_table(cudaStream_t s, const float* emb_a, int stride_a, const float* emb_b, int stride_b, int U, const float* Pa,
+                              const float* Pb, const float* c, int n_cols, float* out) {
+  if (U <= 0) return cudaSuccess;
+  dim3 grid((n_cols + 127) / 128, (U + kCondU - 1) / kCondU);
+  cond_table_kernel<<<grid, 128, 0, s>>>(emb_a, stride_a, emb_b, stride_b, U, Pa, Pb, c, n_cols, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mean_pool(cudaStream_t s, const __half* act, int units, int pixels, int C, float* emb) {
+  if (units <= 0) return cudaSuccess;
+  mean_pool_kernel<<<units, 256, 0, s>>>(act, pixels, C, emb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_units_main(cudaStream_t s, const long long* frame_offs, int U, int w0, int nwin, int* frame, int* lo,
+                              int* hi, int* utt) {
+  if (nwin <= 0) return cudaSuccess;
+  units_main_kernel<<<(nwin + 255) / 256, 256, 0, s>>>(frame_offs, U, w0, nwin, frame, lo, hi, utt);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_units_rows(cudaStream_t s, int r0, int n, int rows_per_unit, int* frame, int* lo, int* hi, int* utt) {
+  if (n <= 0) return cudaSuccess;
+  units_rows_kernel<<<(n + 255) / 256, 256, 0, s>>>(r0, n, rows_per_unit, frame, lo, hi, utt);
+  return cudaGetLastError();
+}
+
+}  // namespace nhans
