@@ -1,0 +1,236 @@
+"""Host-side driver of one GPU context (one per GPU, one thread each): thin numpy <-> C-ABI glue.
+
+Everything numerical happens inside libnhans_b200.so; this module only marshals arrays, concatenates
+ragged utterance lists into (data, offsets) pairs and owns pinned staging buffers."""
+from __future__ import annotations
+
+import ctypes
+import json
+
+import numpy as np
+
+from . import _lib, weights as W
+
+N_BINS = 201
+CTX_FRAMES = 200
+KIND_GEMM, KIND_STFT, KIND_ISTFT, KIND_DIRECT, KIND_OTHER = range(5)
+
+
+class NhansError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libnhans_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pack(clips):
+    """List of 1-D int16 arrays -> (concatenated int16, int64 offsets [U+1])."""
+    offs = np.zeros(len(clips) + 1, np.int64)
+    for i, c in enumerate(clips):
+        offs[i + 1] = offs[i] + len(c)
+    data = np.concatenate([np.asarray(c, np.int16) for c in clips]) if clips else np.zeros(0, np.int16)
+    return np.ascontiguousarray(data), offs
+
+
+def unpack(data, offs):
+    return [data[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (asynchronous H2D / D2H copies need it)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = _lib.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        rc = self.lib.nhans_host_alloc(max(self.nbytes, 1), ctypes.byref(p))
+        if rc:
+            raise NhansError(rc, "cudaHostAlloc failed")
+        self.ptr = p
+        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.nhans_host_free(self.ptr)
+            self.ptr = None
+
+
+class Engine:
+    def __init__(self, device=0, variant=W.SELECTIVE_NOISE, win_capacity=0, row_capacity=0):
+        self.lib = _lib.load()
+        self.variant = variant
+        self.device = device
+        h = ctypes.c_void_p()
+        rc = self.lib.nhans_create(device, variant, win_capacity, row_capacity, ctypes.byref(h))
+        if rc:
+            raise NhansError(rc, self.lib.nhans_last_error(None).decode())
+        self.h = h
+        self.weight_source = None
+
+    # ------------------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise NhansError(rc, self.lib.nhans_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nhans_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_weights(self, weights, source="array"):
+        names = sorted(weights)
+        arrs = [np.ascontiguousarray(weights[n], dtype=np.float32) for n in names]
+        c_names = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
+        c_sizes = (ctypes.c_int64 * len(names))(*[a.size for a in arrs])
+        c_data = (ctypes.c_void_p * len(names))(*[a.ctypes.data for a in arrs])
+        self._ck(self.lib.nhans_load_weights(self.h, c_names, c_sizes, c_data, len(names)))
+        self.weight_source = source
+
+    def load_default_weights(self, model_dir=None, seed=0):
+        w, src = W.load_or_init(self.variant, model_dir, seed)
+        self.load_weights(w, src)
+        return src
+
+    # ---- stage-level --------------------------------------------------------------------------
+    def normalise(self, clips, trim=True):
+        data, offs = pack(clips)
+        out = np.zeros(int(offs[-1]), np.float32)
+        out_offs = np.zeros(len(clips) + 1, np.int64)
+        self._ck(self.lib.nhans_normalise(self.h, _ptr(data), _ptr(offs), len(clips), int(trim), _ptr(out), _ptr(out_offs)))
+        return [out[out_offs[i]:out_offs[i + 1]] for i in range(len(clips))]
+
+    def stft(self, clips):
+        """-> (logmag [F,201], phase [F,201], frame_offs [U+1], peak [U])"""
+        data, offs = pack(clips)
+        U = len(clips)
+        fo = np.zeros(U + 1, np.int64)
+        self._ck(self.lib.nhans_stft(self.h, _ptr(data), _ptr(offs), U, None, None, _ptr(fo), None))
+        F = int(fo[-1])
+        lm = np.zeros((F, N_BINS), np.float32)
+        ph = np.zeros((F, N_BINS), np.float32)
+        peak = np.zeros(U, np.int32)
+        self._ck(self.lib.nhans_stft(self.h, _ptr(data), _ptr(offs), U, _ptr(lm), _ptr(ph), _ptr(fo), _ptr(peak)))
+        return lm, ph, fo, peak
+
+    def embed(self, ctx_logmag):
+        x = np.ascontiguousarray(ctx_logmag, np.float32).reshape(-1, CTX_FRAMES, N_BINS)
+        emb = np.zeros((x.shape[0], 512), np.float32)
+        self._ck(self.lib.nhans_embed(self.h, _ptr(x), x.shape[0], _ptr(emb)))
+        return emb
+
+    def masknet(self, logmag, frame_offs, emb_a, emb_b):
+        lm = np.ascontiguousarray(logmag, np.float32)
+        fo = np.ascontiguousarray(frame_offs, np.int64)
+        ea = np.ascontiguousarray(emb_a, np.float32)
+        eb = np.ascontiguousarray(emb_b, np.float32)
+        out = np.zeros_like(lm)
+        self._ck(self.lib.nhans_masknet(self.h, _ptr(lm), _ptr(fo), len(fo) - 1, _ptr(ea), _ptr(eb), _ptr(out)))
+        return out
+
+    def istft(self, logmag, phase, frame_offs, peak=None, want_i16=False):
+        lm = np.ascontiguousarray(logmag, np.float32)
+        ph = np.ascontiguousarray(phase, np.float32)
+        fo = np.ascontiguousarray(frame_offs, np.int64)
+        U = len(fo) - 1
+        oo = np.zeros(U + 1, np.int64)
+        self._ck(self.lib.nhans_istft(self.h, _ptr(lm), _ptr(ph), _ptr(fo), U, None, None, None, _ptr(oo)))
+        f32 = np.zeros(int(oo[-1]), np.float32)
+        i16 = np.zeros(int(oo[-1]), np.int16) if want_i16 else None
+        pk = np.ascontiguousarray(peak, np.int32) if peak is not None else None
+        self._ck(self.lib.nhans_istft(self.h, _ptr(lm), _ptr(ph), _ptr(fo), U, _ptr(pk), _ptr(f32), _ptr(i16), _ptr(oo)))
+        return (f32, i16, oo) if want_i16 else (f32, oo)
+
+    # ---- fused path ---------------------------------------------------------------------------
+    def output_offsets(self, mix_offs):
+        oo = np.zeros(len(mix_offs), np.int64)
+        rc = self.lib.nhans_output_offsets(_ptr(np.ascontiguousarray(mix_offs, np.int64)), len(mix_offs) - 1, _ptr(oo))
+        if rc:
+            raise NhansError(rc, "bad offsets")
+        return oo
+
+    def enhance_packed(self, mix, mix_offs, ctx_a, a_offs, ctx_b, b_offs, out_i16=None, out_f32=None, mixproc=None, sync=True):
+        """Raw (data, offsets) interface used by the benchmark: enqueue H2D + kernels + D2H."""
+        U = len(mix_offs) - 1
+        self._ck(self.lib.nhans_enhance_batch(self.h, _ptr(mix), _ptr(mix_offs), U, _ptr(ctx_a), _ptr(a_offs), _ptr(ctx_b),
+                                              _ptr(b_offs), _ptr(out_i16), _ptr(out_f32), _ptr(mixproc)))
+        if sync:
+            self.sync()
+
+    def enhance(self, mix_clips, ctx_a_clips, ctx_b_clips, want_f32=True, want_i16=True, want_mixproc=False):
+        """Lists of int16 clips -> dict of per-utterance outputs.  ctx_a_clips may be None (Silent.wav)."""
+        mix, mo = pack(mix_clips)
+        b, bo = pack(ctx_b_clips)
+        a, ao = pack(ctx_a_clips) if ctx_a_clips is not None else (None, None)
+        oo = self.output_offsets(mo)
+        n = int(oo[-1])
+        o16 = np.zeros(n, np.int16) if want_i16 else None
+        o32 = np.zeros(n, np.float32) if want_f32 else None
+        mp = np.zeros(n, np.float32) if want_mixproc else None
+        self.enhance_packed(mix, mo, a, ao, b, bo, o16, o32, mp)
+        res = {"out_offs": oo}
+        if want_i16:
+            res["i16"] = unpack(o16, oo)
+        if want_f32:
+            res["f32"] = unpack(o32, oo)
+        if want_mixproc:
+            res["mixed_processed"] = unpack(mp, oo)
+        return res
+
+    def upload(self, mix, mix_offs, ctx_a, a_offs, ctx_b, b_offs):
+        self._ck(self.lib.nhans_upload(self.h, _ptr(mix), _ptr(mix_offs), len(mix_offs) - 1, _ptr(ctx_a), _ptr(a_offs),
+                                       _ptr(ctx_b), _ptr(b_offs)))
+
+    def run(self):
+        self._ck(self.lib.nhans_run(self.h))
+
+    def download(self, out_i16=None, out_f32=None, mixproc=None):
+        self._ck(self.lib.nhans_download(self.h, _ptr(out_i16), _ptr(out_f32), _ptr(mixproc)))
+
+    def sync(self):
+        self._ck(self.lib.nhans_sync(self.h))
+
+    # ---- measurement / introspection ------------------------------------------------------------
+    def event_record(self, slot):
+        self._ck(self.lib.nhans_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = ctypes.c_double()
+        self._ck(self.lib.nhans_event_elapsed_ms(self.h, a, b, ctypes.byref(ms)))
+        return ms.value
+
+    def profile(self, on=True):
+        self._ck(self.lib.nhans_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._ck(self.lib.nhans_profile_reset(self.h))
+
+    def profile_get(self, kind):
+        st = np.zeros(4, np.float64)
+        self._ck(self.lib.nhans_profile_get(self.h, kind, _ptr(st)))
+        return dict(launches=int(st[0]), ms=float(st[1]), flops=float(st[2]), bytes=float(st[3]))
+
+    def plan(self, net=0):
+        return json.loads(self.lib.nhans_plan_json(self.h, net).decode())
+
+    def read_buffer(self, net, buf):
+        g = self.plan(net)["bufs"][buf]
+        n = g["pixels"] * g["C"]
+        out = np.zeros(n, np.uint16)
+        self._ck(self.lib.nhans_debug_read_buffer(self.h, net, buf, _ptr(out), n))
+        return out.view(np.float16).reshape(g["pixels"], g["C"])
+
+    def device_info(self):
+        sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        self._ck(self.lib.nhans_device_info(self.h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(mem)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), mem_bytes=mem.value)
