@@ -1,0 +1,170 @@
+"""Drop-in mirror of N_HANS___Selective_Noise/apply.py on the B200 engine.
+
+Same entry points, argument meaning and file side effects as the reference:
+``apply_denoiser(mixedpath, negpath, save_to)`` (SN/apply.py:478-481), ``apply_snc(mixedpath, pospath,
+negpath, save_to)`` (:339-472), ``recover_samples_from_spectrum`` (:189-204), ``handle_signals`` (:142-167),
+``read_wav`` (:46-53), flags ``--input --neg --pos --output --compensate --ac`` (:29-35), plus the folder
+mode the README advertises (README.md:59-66) and the ``main()`` the console script expects (setup.py:46).
+All arithmetic runs in libnhans_b200.so on the GPU; there is no TensorFlow and no CPU fallback.
+
+Differences from the reference, all deliberate: wav outputs are 16-bit PCM by
+default (the north-star surface; ``--float32`` / ``out_format='float32'`` restores the reference's
+float32 files), scaled back by the input peak that ``handle_signals`` divided out; a whole folder is
+processed as one GPU batch."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from .. import weights as W
+from ..session import get_engine
+from ..wavio import FS, read_wav, write_wav
+
+Noise_Win = 200      # SN/apply.py:37
+Mix_Win = 35         # SN/apply.py:38
+VARIANT = W.SELECTIVE_NOISE
+_SILENT = "Silent.wav"
+
+
+class _Flags:        # the absl FLAGS of SN/apply.py:29-35
+    input = "./audio_examples/mixed.wav"
+    neg = "./audio_examples/game_noise.wav"
+    pos = "./audio_examples/Silent.wav"
+    output = "./audio_examples/denoised.wav"
+    compensate = 0.0
+    ac = False
+    Fs = FS
+    float32 = False
+
+
+FLAGS = _Flags()
+
+
+def handle_signals(mixedpath, noisepospath, noisenegpath):
+    """SN/apply.py:142-163: (pos, neg, mixed) peak-normalised float32, the mixture trimmed to whole frames."""
+    eng = get_engine(VARIANT)
+    mixed = eng.normalise([read_wav(mixedpath)], trim=True)[0]
+    pos = eng.normalise([read_wav(noisepospath)], trim=False)[0]
+    neg = eng.normalise([read_wav(noisenegpath)], trim=False)[0]
+    return pos, neg, mixed
+
+
+def recover_samples_from_spectrum(logspectrum_stft, spectrum_phase, save_to):
+    """SN/apply.py:189-204: log-magnitude + phase -> samples (float32), written to ``save_to`` as float32 wav."""
+    eng = get_engine(VARIANT)
+    lm = np.ascontiguousarray(logspectrum_stft, np.float32)
+    samples, _ = eng.istft(lm, spectrum_phase, np.array([0, lm.shape[0]], np.int64))
+    if save_to:
+        write_wav(save_to, samples)
+    return samples
+
+
+def _is_silent(path):
+    return path is None or os.path.basename(path) == _SILENT
+
+
+def _sibling(save_to, name):
+    # the reference derives the extra outputs with save_to[:-12] (assumes '...denoised.wav', SN/apply.py:457)
+    if save_to.endswith("denoised.wav"):
+        return save_to[:-12] + name
+    root, _ = os.path.splitext(save_to)
+    return root + "_" + name
+
+
+def _emit(save_to, f32, peak, as_float32):
+    if as_float32:
+        write_wav(save_to, f32.astype(np.float32))
+    else:
+        v = np.rint(f32.astype(np.float32) * np.float32(peak + 0.000001))
+        write_wav(save_to, np.clip(v, -32768, 32767).astype(np.int16))
+
+
+def apply_snc_batch(mixedpaths, pospaths, negpaths, save_tos, compensate=None, ac=None, out_format=None):
+    """apply_snc for many files in one GPU batch (folder mode).  pospaths entries may be None / Silent.wav."""
+    compensate = FLAGS.compensate if compensate is None else compensate
+    ac = FLAGS.ac if ac is None else ac
+    as_f32 = (FLAGS.float32 if out_format is None else out_format == "float32")
+    eng = get_engine(VARIANT)
+    mixes = [read_wav(p) for p in mixedpaths]
+    negs = [read_wav(p) for p in negpaths]
+    all_silent = all(_is_silent(p) for p in pospaths)
+    poss = None if all_silent else [read_wav(p) for p in pospaths]
+    res = eng.enhance(mixes, poss, negs, want_f32=True, want_i16=False, want_mixproc=True)
+    snrs = []
+    for u, save_to in enumerate(save_tos):
+        den = res["f32"][u]
+        mixed = res["mixed_processed"][u]
+        peak = float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0
+        _emit(save_to, den, peak, as_f32)
+        _emit(_sibling(save_to, "mixed_processed.wav"), mixed, peak, as_f32)
+        removed = mixed - den                                            # SN/apply.py:460
+        _emit(_sibling(save_to, "removed.wav"), removed, peak, as_f32)
+        denom = float(np.mean(np.square(removed))) if len(removed) else 0.0
+        snr_est = float(np.mean(np.square(den))) / denom if denom > 0 else float("inf")   # SN/apply.py:463
+        print(snr_est)
+        print("---------------------------")
+        factor = snr_est / 20 if ac else compensate                      # SN/apply.py:466-469
+        if not np.isfinite(factor):
+            factor = 0.0
+        _emit(_sibling(save_to, "compensated.wav"), den + removed * factor, peak, as_f32)
+        snrs.append(snr_est)
+    return snrs
+
+
+def apply_snc(mixedpath, pospath, negpath, save_to):
+    """SN/apply.py:339-472: selective noise suppression conditioned on a positive and a negative recording."""
+    apply_snc_batch([mixedpath], [pospath], [negpath], [save_to])
+
+
+def apply_denoiser(mixedpath, negpath, save_to):
+    """SN/apply.py:478-481: pure denoising; the positive context is the all-zero Silent.wav, whose embedding
+    is a per-model constant the engine caches."""
+    apply_snc(mixedpath, None, negpath, save_to)
+
+
+def _pairs(inp, pos, neg, out):
+    """README.md:59-66 folder mode: files with identical names in the input / pos / neg folders."""
+    names = sorted(f for f in os.listdir(inp) if f.lower().endswith(".wav"))
+    os.makedirs(out, exist_ok=True)
+    mixed, poss, negs, outs = [], [], [], []
+    for n in names:
+        npth = os.path.join(neg, n)
+        if not os.path.exists(npth):
+            sys.stderr.write("skipping %s: no --neg file of the same name\n" % n)
+            continue
+        mixed.append(os.path.join(inp, n))
+        negs.append(npth)
+        ppth = os.path.join(pos, n) if pos and os.path.isdir(pos) else None
+        poss.append(ppth if ppth and os.path.exists(ppth) else None)
+        outs.append(os.path.join(out, n[:-4] + "_denoised.wav"))
+    return mixed, poss, negs, outs
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="nhans_denoiser", description="N-HANS denoiser / selective noise suppression (B200 engine)")
+    ap.add_argument("--input", default=FLAGS.input)
+    ap.add_argument("--neg", default=FLAGS.neg)
+    ap.add_argument("--pos", default=FLAGS.pos)
+    ap.add_argument("--output", default=FLAGS.output)
+    ap.add_argument("--compensate", type=float, default=0.0)
+    ap.add_argument("--ac", action="store_true")
+    ap.add_argument("--float32", action="store_true", help="write float32 wavs like the reference instead of 16-bit PCM")
+    a = ap.parse_args(argv)
+    FLAGS.input, FLAGS.neg, FLAGS.pos, FLAGS.output = a.input, a.neg, a.pos, a.output
+    FLAGS.compensate, FLAGS.ac, FLAGS.float32 = a.compensate, a.ac, a.float32
+    if os.path.isdir(a.input):
+        mixed, poss, negs, outs = _pairs(a.input, a.pos, a.neg, a.output)
+        if mixed:
+            apply_snc_batch(mixed, poss, negs, outs)
+    elif _is_silent(a.pos):
+        apply_denoiser(a.input, a.neg, a.output)
+    else:
+        apply_snc(a.input, a.pos, a.neg, a.output)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

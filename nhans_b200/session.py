@@ -1,0 +1,35 @@
+"""Process-wide engine cache used by the apply.py mirrors and the CLIs: one context per (device, variant),
+weights restored from the reference checkpoint directory when it holds real blobs, else the seeded random
+initialisation of the identical architecture (the reference restores './trained_model/<ckpt>' on every
+call, N_HANS___Selective_Noise/apply.py:430-432; here it happens once per process)."""
+from __future__ import annotations
+
+import os
+import sys
+
+from . import weights as W
+from .engine import Engine
+
+_ENGINES = {}
+
+
+def get_engine(variant, device=None, model_dir=None):
+    device = int(os.environ.get("NHANS_DEVICE", "0")) if device is None else device
+    key = (device, variant)
+    if key not in _ENGINES:
+        model_dir = model_dir or os.environ.get("NHANS_MODEL_DIR", "./trained_model")
+        eng = Engine(device, variant,
+                     win_capacity=int(os.environ.get("NHANS_WIN_CAPACITY", "0")),
+                     row_capacity=int(os.environ.get("NHANS_ROW_CAPACITY", "0")))
+        src = eng.load_default_weights(model_dir, seed=int(os.environ.get("NHANS_SEED", "0")))
+        if src != "checkpoint":
+            sys.stderr.write("nhans_b200: no trained checkpoint under %r (git-LFS pointer or absent); "
+                             "using seeded random-init weights of the identical architecture\n" % model_dir)
+        _ENGINES[key] = eng
+    return _ENGINES[key]
+
+
+def close_all():
+    for e in _ENGINES.values():
+        e.close()
+    _ENGINES.clear()

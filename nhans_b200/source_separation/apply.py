@@ -1,0 +1,98 @@
+"""Drop-in mirror of N_HANS___Source_Separation/apply.py on the B200 engine.
+
+``apply_separator(mixedpath, cleanpath, noisepath, save_to)`` (SS/apply.py:288-397) with the flags
+``--input --pos(target speaker) --neg(interference speaker) --output`` (SS/apply.py:28-34), folder mode
+(README.md:59-66) and ``main()`` (setup.py:48).  The reference feeds ``noisecontextph`` from --neg and
+``cleancontextph`` from --pos (SS/apply.py:374-385); the engine calls them ctx_a / ctx_b.  It writes the
+separated wav and '<...>mixed_processed.wav' (SS/apply.py:395-397)."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from .. import weights as W
+from ..session import get_engine
+from ..wavio import FS, read_wav, write_wav
+from ..selective_noise.apply import _emit, _sibling
+
+Noise_Win = 200
+Mix_Win = 35
+VARIANT = W.SEPARATOR
+
+
+class _Flags:        # SS/apply.py:28-34
+    input = "./audio_examples/mixed.wav"
+    neg = "./audio_examples/noise_speaker.wav"
+    pos = "./audio_examples/target_speaker.wav"
+    output = "./audio_examples/denoised.wav"
+    Fs = FS
+    float32 = False
+
+
+FLAGS = _Flags()
+
+
+def handle_signals(mixedpath, cleanpath, noisepath):
+    """SS/apply.py:111-136."""
+    eng = get_engine(VARIANT)
+    mixed = eng.normalise([read_wav(mixedpath)], trim=True)[0]
+    clean = eng.normalise([read_wav(cleanpath)], trim=False)[0]
+    noise = eng.normalise([read_wav(noisepath)], trim=False)[0]
+    return clean, noise, mixed
+
+
+def recover_samples_from_spectrum(logspectrum_stft, spectrum_phase, save_to):
+    """SS/apply.py:158-171."""
+    eng = get_engine(VARIANT)
+    lm = np.ascontiguousarray(logspectrum_stft, np.float32)
+    samples, _ = eng.istft(lm, spectrum_phase, np.array([0, lm.shape[0]], np.int64))
+    if save_to:
+        write_wav(save_to, samples)
+    return samples
+
+
+def apply_separator_batch(mixedpaths, cleanpaths, noisepaths, save_tos, out_format=None):
+    as_f32 = (FLAGS.float32 if out_format is None else out_format == "float32")
+    eng = get_engine(VARIANT)
+    mixes = [read_wav(p) for p in mixedpaths]
+    cleans = [read_wav(p) for p in cleanpaths]
+    noises = [read_wav(p) for p in noisepaths]
+    res = eng.enhance(mixes, noises, cleans, want_f32=True, want_i16=False, want_mixproc=True)   # ctx_a = --neg, ctx_b = --pos
+    for u, save_to in enumerate(save_tos):
+        peak = float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0
+        _emit(save_to, res["f32"][u], peak, as_f32)
+        _emit(_sibling(save_to, "mixed_processed.wav"), res["mixed_processed"][u], peak, as_f32)
+
+
+def apply_separator(mixedpath, cleanpath, noisepath, save_to):
+    """SS/apply.py:288-397: extract the speaker of ``cleanpath`` (--pos), suppress the one of ``noisepath`` (--neg)."""
+    apply_separator_batch([mixedpath], [cleanpath], [noisepath], [save_to])
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="nhans_separator", description="N-HANS speech separator (B200 engine)")
+    ap.add_argument("--input", default=FLAGS.input)
+    ap.add_argument("--neg", default=FLAGS.neg)
+    ap.add_argument("--pos", default=FLAGS.pos)
+    ap.add_argument("--output", default=FLAGS.output)
+    ap.add_argument("--float32", action="store_true")
+    a = ap.parse_args(argv)
+    FLAGS.input, FLAGS.neg, FLAGS.pos, FLAGS.output, FLAGS.float32 = a.input, a.neg, a.pos, a.output, a.float32
+    if os.path.isdir(a.input):
+        names = sorted(f for f in os.listdir(a.input) if f.lower().endswith(".wav"))
+        os.makedirs(a.output, exist_ok=True)
+        names = [n for n in names if os.path.exists(os.path.join(a.pos, n)) and os.path.exists(os.path.join(a.neg, n))]
+        if names:
+            apply_separator_batch([os.path.join(a.input, n) for n in names], [os.path.join(a.pos, n) for n in names],
+                                  [os.path.join(a.neg, n) for n in names],
+                                  [os.path.join(a.output, n[:-4] + "_denoised.wav") for n in names])
+    else:
+        apply_separator(a.input, a.pos, a.neg, a.output)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
