@@ -107,8 +107,9 @@ int nhans_event_record(nhans_ctx* ctx, int slot);
 int nhans_event_elapsed_ms(nhans_ctx* ctx, int start_slot, int stop_slot, double* ms);
 
 /* Per-kernel statistics gathered with CUDA events around every launch while enabled (adds a few us per
- * launch).  kind: 0 tensor-core GEMM layers, 1 STFT, 2 iSTFT, 3 direct (Cin = 1) convolutions, 4 other.
- * stats [4] = {launches, total_ms, algorithmic_flops, algorithmic_bytes}. */
+ * launch).  kind: 0 tensor-core GEMM layers, 1 STFT, 2 iSTFT, 3 direct (Cin = 1) convolutions, 4 other;
+ * stats [4] = {launches, total_ms, algorithmic_flops, algorithmic_bytes}.  kind 5: stats[0] = every kernel
+ * this context launched since the last reset (counted whether or not profiling is enabled). */
 int nhans_profile_enable(nhans_ctx* ctx, int on);
 int nhans_profile_get(nhans_ctx* ctx, int kind, double* stats);
 int nhans_profile_reset(nhans_ctx* ctx);

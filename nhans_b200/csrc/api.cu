@@ -104,6 +104,7 @@ struct nhans_ctx {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   double prof_acc[5][4] = {};
+  double launches = 0;              // every kernel launched by this context (counted even when not profiling)
 };
 
 namespace {
@@ -235,6 +236,7 @@ struct ProfScope {
   bool on;
   ProfRec r;
   ProfScope(nhans_ctx* c, int kind, double flops, double bytes) : ctx(c), on(c->profile) {
+    c->launches += 1;
     if (!on) return;
     r.kind = kind; r.flops = flops; r.bytes = bytes;
     r.a = get_event(c); r.b = get_event(c);
@@ -339,6 +341,7 @@ int run_tower(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb) {
   for (int r0 = 0; r0 < R; r0 += cap) {
     const int n = std::min(cap, R - r0);
     CK(launch_units_rows(ctx->stream, r0, n, kCtxFrames, net.u_frame, net.u_lo, net.u_hi, net.u_utt));
+    ctx->launches += 1;
     int rc = run_net(ctx, net, n, ctx_logmag, nullptr, nullptr);
     if (rc) return rc;
     ProfScope ps(ctx, 4, 0, 0);
@@ -356,6 +359,7 @@ int run_masknet(nhans_ctx* ctx, const float* logmag, const long long* d_frame_of
   for (long long w0 = 0; w0 < total_frames; w0 += cap) {
     const int n = (int)std::min<long long>(cap, total_frames - w0);
     CK(launch_units_main(ctx->stream, d_frame_offs, U, (int)w0, n, net.u_frame, net.u_lo, net.u_hi, net.u_utt));
+    ctx->launches += 1;
     int rc = run_net(ctx, net, n, logmag, cond_table, den + (size_t)w0 * kBins);
     if (rc) return rc;
   }
@@ -733,6 +737,7 @@ int nhans_run(nhans_ctx* ctx) {
   // front end: a2-a4 for the mixture and the first 200 frames of each context (SN/apply.py:359-387)
   CK(launch_peaks(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), U, b.peak_mix.as<int>()));
   CK(launch_peaks(ctx->stream, b.b.as<int16_t>(), b.d_b_offs.as<long long>(), U, b.peak_b.as<int>()));
+  ctx->launches += 2;
   {
     ProfScope ps(ctx, 1, 0, 2.0 * b.mix_offs[U] + 2.0 * sbytes);
     CK(launch_stft(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), b.d_frame_offs.as<long long>(), U,
@@ -749,6 +754,7 @@ int nhans_run(nhans_ctx* ctx) {
     CK(b.ctxlm_a.ensure(cbytes));
     CK(b.emb_a.ensure((size_t)U * 512 * 4));
     CK(launch_peaks(ctx->stream, b.a.as<int16_t>(), b.d_a_offs.as<long long>(), U, b.peak_a.as<int>()));
+    ctx->launches += 1;
     ProfScope ps(ctx, 4, 0, 0);
     CK(launch_stft(ctx->stream, b.a.as<int16_t>(), b.d_a_offs.as<long long>(), b.d_ctx_frame_offs.as<long long>(), U,
                    b.peak_a.as<int>(), kCtxFrames, (long long)U * kCtxFrames, b.ctxlm_a.as<float>(), nullptr));
@@ -848,9 +854,13 @@ int nhans_profile_enable(nhans_ctx* ctx, int on) {
   return NHANS_OK;
 }
 int nhans_profile_get(nhans_ctx* ctx, int kind, double* stats) {
-  if (!ctx || !stats || kind < 0 || kind > 4) return NHANS_ERR_ARG;
+  if (!ctx || !stats || kind < 0 || kind > 5) return NHANS_ERR_ARG;
   cudaSetDevice(ctx->device);
   prof_collect(ctx);
+  if (kind == 5) {
+    stats[0] = ctx->launches; stats[1] = stats[2] = stats[3] = 0;
+    return NHANS_OK;
+  }
   for (int i = 0; i < 4; ++i) stats[i] = ctx->prof_acc[kind][i];
   return NHANS_OK;
 }
@@ -859,6 +869,7 @@ int nhans_profile_reset(nhans_ctx* ctx) {
   cudaSetDevice(ctx->device);
   prof_collect(ctx);
   memset(ctx->prof_acc, 0, sizeof ctx->prof_acc);
+  ctx->launches = 0;
   return NHANS_OK;
 }
 

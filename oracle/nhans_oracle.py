@@ -273,10 +273,9 @@ def istft(logmag, phase):
 
 def to_int16(y, peak):
     """New-repo convention (not reference behaviour): undo the peak normalisation of
-    SN/apply.py:150, round half away from zero, saturate."""
-    v = np.asarray(y, np.float64) * (peak + 0.000001)
-    v = np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5))
-    return np.clip(v, -32768, 32767).astype(np.int16)
+    SN/apply.py:150 in float32, round half to even, saturate."""
+    v = np.asarray(y, np.float32) * np.float32(peak + 0.000001)
+    return np.clip(np.rint(v), -32768, 32767).astype(np.int16)
 
 
 # ---------------------------------------------------------------------------------------------

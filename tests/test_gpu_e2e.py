@@ -1,0 +1,143 @@
+"""End-to-end apply path through nhans_enhance_batch: SNR >= 40 dB against the oracle's apply_snc /
+apply_separator restatement, golden vectors, batch invariance, error behaviour, CLI file surface."""
+import os
+
+import numpy as np
+import pytest
+
+from nhans_b200 import synth, weights as W
+from nhans_b200.engine import Engine, NhansError
+from oracle import nhans_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SNR_MIN_DB = 40.0
+
+
+def _snr(ref, got):
+    ref = ref.astype(np.float64)
+    err = got.astype(np.float64) - ref
+    return 10 * np.log10(np.sum(ref ** 2) / (np.sum(err ** 2) + 1e-30))
+
+
+def test_denoiser_snr_vs_oracle(engine_sn, oracle_sn):
+    mixes = [synth.mixture(1.0, 0), synth.mixture(0.6, 1), synth.mixture(0.35, 2)]      # ragged batch
+    negs = [synth.noise_clip(u) for u in range(3)]
+    res = engine_sn.enhance(mixes, None, negs, want_mixproc=True)
+    for u in range(3):
+        r = O.apply_arrays(oracle_sn, mixes[u], synth.silence(), negs[u], return_all=True)
+        assert len(res["f32"][u]) == len(r["samples"])
+        assert _snr(r["samples"], res["f32"][u]) >= SNR_MIN_DB
+        assert np.abs(res["mixed_processed"][u] - r["mixed_processed"]).max() < 1e-5
+        i16 = O.to_int16(r["samples"], r["peak"]).astype(np.int32)
+        assert np.abs(res["i16"][u].astype(np.int32) - i16).max() <= max(2, int(3e-3 * np.abs(i16).max()))
+
+
+def test_selective_noise_pos_and_neg(engine_sn, oracle_sn):
+    mix, pos, neg = synth.mixture(0.5, 4), synth.noise_clip(4, "pos"), synth.noise_clip(4, "neg")
+    res = engine_sn.enhance([mix], [pos], [neg])
+    ref = O.apply_arrays(oracle_sn, mix, pos, neg)
+    assert _snr(ref, res["f32"][0]) >= SNR_MIN_DB
+
+
+def test_separator_snr_vs_oracle(engine_ss, oracle_ss):
+    mix = synth.mixture(0.5, 6)
+    tgt, itf = synth.speaker_clip(6, "target"), synth.speaker_clip(6, "interference")
+    res = engine_ss.enhance([mix], [itf], [tgt])                     # ctx_a = --neg (interference), ctx_b = --pos (target)
+    ref = O.apply_arrays(oracle_ss, mix, itf, tgt)
+    assert _snr(ref, res["f32"][0]) >= SNR_MIN_DB
+    with pytest.raises(NhansError):                                  # the separator has no Silent default
+        engine_ss.enhance([mix], None, [tgt])
+
+
+@pytest.mark.parametrize("tag", ["sn", "ss"])
+def test_golden_vectors(tag, engine_sn, engine_ss):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(GOLD, "golden_%s.npz" % tag))
+    eng = engine_sn if tag == "sn" else engine_ss
+    mix, a, b = mg.inputs(tag)
+    lm, ph, fo, _ = eng.stft([mix])
+    assert np.abs(lm - g["logmag"]).max() < 1e-3
+    res = eng.enhance([mix], None if tag == "sn" else [a], [b], want_mixproc=True)
+    assert _snr(g["samples"], res["f32"][0]) >= SNR_MIN_DB
+    assert np.abs(res["mixed_processed"][0] - g["mixed_processed"]).max() < 1e-5
+
+
+def test_batch_invariance_and_chunking(engine_sn):
+    """An utterance's output does not depend on its position in the batch or on the pass boundaries."""
+    mixes = [synth.mixture(0.3 + 0.05 * (u % 5), u) for u in range(12)]       # ~470 windows, capacity 256 -> 2 passes
+    negs = [synth.noise_clip(u % 3) for u in range(12)]
+    res = engine_sn.enhance(mixes, None, negs)
+    for u in (0, 5, 11):
+        solo = engine_sn.enhance([mixes[u]], None, [negs[u]])
+        assert np.array_equal(solo["i16"][0], res["i16"][u])
+        assert np.array_equal(solo["f32"][0], res["f32"][u])
+
+
+def test_zero_last_dense_identity(weights_sn):
+    """with last_dense == 0 the denoised wav equals mixed_processed.wav exactly."""
+    w = dict(weights_sn)
+    w["last_dense/w"] = np.zeros_like(w["last_dense/w"])
+    w["last_dense/b"] = np.zeros_like(w["last_dense/b"])
+    eng = Engine(0, 0, win_capacity=64, row_capacity=1)
+    eng.load_weights(w)
+    res = eng.enhance([synth.mixture(0.4, 8)], None, [synth.noise_clip(8)], want_mixproc=True)
+    assert np.array_equal(res["f32"][0], res["mixed_processed"][0])
+    eng.close()
+
+
+def test_error_behaviour(engine_sn):
+    with pytest.raises(NhansError) as ei:                             # 1 s context: < 200 frames
+        engine_sn.enhance([synth.mixture(0.3, 0)], None, [synth.noise_clip(0, seconds=1.0)])
+    assert ei.value.code == -4
+    res = engine_sn.enhance([synth.mixture(0.3, 0)[:300], synth.mixture(0.3, 1)], None, [synth.noise_clip(0), synth.noise_clip(1)])
+    assert len(res["f32"][0]) == 0 and len(res["f32"][1]) == O.trim_len(4800)     # < 400 samples -> no frames, empty output
+    eng = Engine(0, 0, win_capacity=8, row_capacity=1)
+    with pytest.raises(NhansError):                                   # weights not loaded
+        eng.enhance([synth.mixture(0.3, 0)], None, [synth.noise_clip(0)])
+    with pytest.raises(NhansError):
+        eng.load_weights({"last_dense/w": np.zeros((3, 3), np.float32)})
+    eng.close()
+
+
+def test_cli_file_surface(tmp_path, monkeypatch):
+    """nhans_denoiser / nhans_separator: 16 kHz 16-bit PCM in and out, the four SN outputs, folder mode."""
+    from nhans_b200 import session
+    from nhans_b200.selective_noise import apply as sn_apply
+    from nhans_b200.source_separation import apply as ss_apply
+    from nhans_b200.wavio import read_wav, write_wav
+    monkeypatch.setenv("NHANS_WIN_CAPACITY", "128")
+    monkeypatch.setenv("NHANS_ROW_CAPACITY", "2")
+    monkeypatch.setenv("NHANS_MODEL_DIR", str(tmp_path / "no_model"))
+    session.close_all()
+    d = tmp_path
+    write_wav(str(d / "mixed.wav"), synth.mixture(0.5, 0))
+    write_wav(str(d / "noise.wav"), synth.noise_clip(0))
+    write_wav(str(d / "pos.wav"), synth.noise_clip(0, "pos"))
+    out = str(d / "out_denoised.wav")
+    assert sn_apply.main(["--input", str(d / "mixed.wav"), "--neg", str(d / "noise.wav"), "--output", out]) == 0
+    for name in ("out_denoised.wav", "out_mixed_processed.wav", "out_removed.wav", "out_compensated.wav"):
+        y = read_wav(str(d / name))                                   # asserts 16 kHz int16
+        assert len(y) == O.trim_len(8000)
+    a = read_wav(out)
+    sn_apply.apply_snc(str(d / "mixed.wav"), str(d / "pos.wav"), str(d / "noise.wav"), str(d / "snc_denoised.wav"))
+    assert not np.array_equal(read_wav(str(d / "snc_denoised.wav")), a)          # the --pos context matters
+    # folder mode (README.md:59-66)
+    for sub in ("in", "neg"):
+        os.makedirs(str(d / sub))
+    for n in ("a.wav", "b.wav"):
+        write_wav(str(d / "in" / n), synth.mixture(0.3, 3))
+        write_wav(str(d / "neg" / n), synth.noise_clip(3))
+    assert sn_apply.main(["--input", str(d / "in"), "--neg", str(d / "neg"), "--output", str(d / "outdir")]) == 0
+    assert sorted(f for f in os.listdir(str(d / "outdir")) if f.endswith("_denoised.wav")) == ["a_denoised.wav", "b_denoised.wav"]
+    write_wav(str(d / "tgt.wav"), synth.speaker_clip(1, "target"))
+    write_wav(str(d / "itf.wav"), synth.speaker_clip(1, "interference"))
+    assert ss_apply.main(["--input", str(d / "mixed.wav"), "--pos", str(d / "tgt.wav"), "--neg", str(d / "itf.wav"),
+                          "--output", str(d / "sep_denoised.wav"), "--float32"]) == 0
+    from scipy.io.wavfile import read
+    rate, y = read(str(d / "sep_denoised.wav"))
+    assert rate == 16000 and y.dtype == np.float32                    # the reference's own output format
+    session.close_all()

@@ -1,0 +1,84 @@
+"""tcgen05 network kernels through the C ABI: tight against the CPU plan interpreter (same fp16 data
+path), and within the stated tolerance against the fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from nhans_b200 import synth
+from oracle import nhans_oracle as O
+from oracle.planexec import PlanExec, grid_gather
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3            # relative (Frobenius) error of embeddings / mask vs the fp32 oracle
+EXEC_TOL = 2e-4           # vs the CPU interpreter of the same fp16 plan (accumulation order only)
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def test_embedding_tower(engine_sn, weights_sn, oracle_sn):
+    ctx = np.stack([O.context_of(O.logmag_phase(O.normalise(synth.noise_clip(u)))[0]) for u in range(6)])   # > row capacity 4
+    emb = engine_sn.embed(ctx)
+    with torch.no_grad():
+        ref = oracle_sn.tower(torch.from_numpy(ctx)).numpy()
+    assert _rel(emb, ref) < REL_TOL
+    pe = PlanExec(weights_sn, 0, win_cap=1, row_cap=1)
+    assert _rel(emb[:2], pe.embed(ctx[:2])) < EXEC_TOL
+    pe.close()
+    sil = np.full((1, 200, 201), np.log(np.float32(1e-5)), np.float32)                                       # Silent.wav context
+    with torch.no_grad():
+        ref = oracle_sn.tower(torch.from_numpy(sil)).numpy()
+    assert _rel(engine_sn.embed(sil), ref) < REL_TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_masknet_layers_and_output(variant, engine_sn, engine_ss, weights_sn, weights_ss, oracle_sn, oracle_ss):
+    eng = engine_sn if variant == 0 else engine_ss
+    w = weights_sn if variant == 0 else weights_ss
+    net = oracle_sn if variant == 0 else oracle_ss
+    mixes = [synth.mixture(0.2, 0)[:400 + 160 * 5], synth.mixture(0.2, 1)[:400 + 160 * 2]]      # 6 + 3 windows
+    lms = [O.logmag_phase(O.normalise(m))[0] for m in mixes]
+    fo = np.cumsum([0] + [l.shape[0] for l in lms])
+    lm = np.concatenate(lms)
+    rng = np.random.default_rng(variant)
+    ea = rng.normal(0, 2, (2, 512)).astype(np.float32)
+    eb = rng.normal(0, 2, (2, 512)).astype(np.float32)
+    den = eng.masknet(lm, fo, ea, eb)
+    pe = PlanExec(w, variant, win_cap=256, row_cap=1)
+    den_pe = pe.masknet(lm, fo, ea, eb)
+    assert _rel(den - lm, den_pe - lm) < 2e-3 and np.abs(den - den_pe).max() < 2e-3
+    plan = eng.plan(0)
+    assert plan["bufs"] == pe.plan(0)["bufs"]
+    for g in plan["bufs"]:                                   # every activation grid, every logical pixel
+        a = grid_gather(g, eng.read_buffer(0, g["buf"]).astype(np.float32), 9)
+        b = grid_gather(g, pe.read_buffer(0, g["buf"]), 9)
+        assert _rel(a, b) < 1e-3, g
+    pe.close()
+    ref = []
+    with torch.no_grad():
+        for u, l in enumerate(lms):
+            win = torch.from_numpy(O.strided_crop(l, 35))
+            T = win.shape[0]
+            ref.append(net.mask_net(win, torch.from_numpy(ea[u:u + 1]).expand(T, -1), torch.from_numpy(eb[u:u + 1]).expand(T, -1)).numpy())
+    ref = np.concatenate(ref)
+    # mask = exp(out): relative mask error == absolute error of out
+    assert _rel(np.exp(den - lm), np.exp(ref - lm)) < REL_TOL
+    assert _rel(den - lm, ref - lm) < 2e-3
+
+
+def test_padding_positions_stay_zero(engine_sn):
+    """The grids' padding slots implement the conv zero padding; no kernel may ever write them."""
+    rng = np.random.default_rng(5)
+    lm = rng.normal(-3, 2, (300, 201)).astype(np.float32)     # > win capacity 256 -> 2 passes
+    engine_sn.masknet(lm, np.array([0, 120, 300]), rng.normal(0, 1, (2, 512)).astype(np.float32), rng.normal(0, 1, (2, 512)).astype(np.float32))
+    plan = engine_sn.plan(0)
+    for g in plan["bufs"]:
+        if g["mode"] != 0:
+            continue
+        buf = engine_sn.read_buffer(0, g["buf"])
+        mask = np.ones(g["pixels"], bool)
+        pix = grid_gather(g, np.arange(g["pixels"])[:, None], plan["capacity"])[..., 0]
+        mask[pix.ravel()] = False
+        assert not np.any(buf[mask]), g
