@@ -194,6 +194,7 @@ def main():
     barrier()
     ms_res = max_over_ranks(eng.event_elapsed_ms(0, 1))
     st = {k: eng.profile_get(k) for k in range(6)}
+    layers = eng.profile_layers(0)
     eng.profile(False)
     clocks = sampler.stop() if rank == 0 else None
     value = world * a.steps * audio_s / (ms_res / 1e3)
@@ -241,6 +242,7 @@ def main():
                           "GBps": st[KIND_ISTFT]["bytes"] / max(st[KIND_ISTFT]["ms"], 1e-9) / 1e6, "frac_hbm": st[KIND_ISTFT]["bytes"] / max(st[KIND_ISTFT]["ms"], 1e-9) / 1e6 / hbm_peak},
                 "direct_conv": {"launches": st[3]["launches"], "ms": st[3]["ms"]},
                 "other": {"launches": st[4]["launches"], "ms": st[4]["ms"]}},
+            "layers": [{"name": l["name"], "ms_per_step": l["ms"] / a.steps, "TFLOPs": round(l["tflops"], 1)} for l in layers],
             "tensor_ceiling_audio_s_per_s": tf_peak * 1e3 / (GFLOP_PER_WINDOW * 100) * world,
         })
         if world == 1 and not a.no_cpu_baseline:

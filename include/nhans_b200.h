@@ -113,6 +113,8 @@ int nhans_event_elapsed_ms(nhans_ctx* ctx, int start_slot, int stop_slot, double
 int nhans_profile_enable(nhans_ctx* ctx, int on);
 int nhans_profile_get(nhans_ctx* ctx, int kind, double* stats);
 int nhans_profile_reset(nhans_ctx* ctx);
+/* The same statistics for one tensor-core layer (net 0 main, 1 tower; layer = index into the plan's gemm list). */
+int nhans_profile_get_layer(nhans_ctx* ctx, int net, int layer, double* stats);
 
 /* ---- introspection (tests) -------------------------------------------------------------------------- */
 

@@ -14,7 +14,8 @@ SYMBOLS = [
     "nhans_create", "nhans_destroy", "nhans_last_error", "nhans_load_weights", "nhans_normalise", "nhans_stft",
     "nhans_embed", "nhans_masknet", "nhans_istft", "nhans_output_offsets", "nhans_enhance_batch", "nhans_sync",
     "nhans_upload", "nhans_run", "nhans_download", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
-    "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset", "nhans_plan_json",
+    "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset",
+    "nhans_profile_get_layer", "nhans_plan_json",
     "nhans_debug_read_buffer", "nhans_device_info",
 ]
 
@@ -67,6 +68,7 @@ def load():
     lib.nhans_profile_enable.argtypes = [vp, i32]
     lib.nhans_profile_get.argtypes = [vp, i32, vp]
     lib.nhans_profile_reset.argtypes = [vp]
+    lib.nhans_profile_get_layer.argtypes = [vp, i32, i32, vp]
     lib.nhans_debug_read_buffer.argtypes = [vp, i32, i32, vp, i64]
     lib.nhans_device_info.argtypes = [vp, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32), c.POINTER(i64)]
     _lib = lib

@@ -66,6 +66,7 @@ struct NetDev {
 
 struct ProfRec {
   int kind;
+  int layer;                        // net * 64 + gemm layer index, or -1
   cudaEvent_t a, b;
   double flops, bytes;
 };
@@ -104,6 +105,8 @@ struct nhans_ctx {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   double prof_acc[5][4] = {};
+  int debug_skip_epilogue = 0;
+  double layer_acc[128][4] = {};
   double launches = 0;              // every kernel launched by this context (counted even when not profiling)
 };
 
@@ -235,10 +238,10 @@ struct ProfScope {
   nhans_ctx* ctx;
   bool on;
   ProfRec r;
-  ProfScope(nhans_ctx* c, int kind, double flops, double bytes) : ctx(c), on(c->profile) {
+  ProfScope(nhans_ctx* c, int kind, double flops, double bytes, int layer = -1) : ctx(c), on(c->profile) {
     c->launches += 1;
     if (!on) return;
-    r.kind = kind; r.flops = flops; r.bytes = bytes;
+    r.kind = kind; r.flops = flops; r.bytes = bytes; r.layer = layer;
     r.a = get_event(c); r.b = get_event(c);
     cudaEventRecord(r.a, c->stream);
   }
@@ -257,6 +260,10 @@ void prof_collect(nhans_ctx* ctx) {
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
       double* a = ctx->prof_acc[r.kind];
       a[0] += 1; a[1] += ms; a[2] += r.flops; a[3] += r.bytes;
+      if (r.layer >= 0 && r.layer < 128) {
+        double* l = ctx->layer_acc[r.layer];
+        l[0] += 1; l[1] += ms; l[2] += r.flops; l[3] += r.bytes;
+      }
     }
     ctx->ev_pool.push_back(r.a);
     ctx->ev_pool.push_back(r.b);
@@ -328,7 +335,8 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.units = ut;
     g.epi = make_epi(net, L.epi, L.out, D.bias, D.ttab, D.ftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);
     g.err_flag = ctx->err_flag_dev;
-    ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0);
+    g.debug_skip_epilogue = ctx->debug_skip_epilogue;
+    ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0, (&net == &ctx->tower ? 64 : 0) + (int)i);
     CK(launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, g));
   }
   return 0;
@@ -432,6 +440,7 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   ctx->variant = variant;
   if (win_capacity > 0) ctx->win_cap = win_capacity;
   if (row_capacity > 0) ctx->row_cap = row_capacity;
+  if (const char* dbg = getenv("NHANS_DEBUG_SKIP_EPILOGUE")) ctx->debug_skip_epilogue = atoi(dbg);
   ctx->n_sm = prop.multiProcessorCount;
   auto bail = [&](const std::string& m) { g_create_error = m; return NHANS_ERR_CUDA; };
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
@@ -869,7 +878,16 @@ int nhans_profile_reset(nhans_ctx* ctx) {
   cudaSetDevice(ctx->device);
   prof_collect(ctx);
   memset(ctx->prof_acc, 0, sizeof ctx->prof_acc);
+  memset(ctx->layer_acc, 0, sizeof ctx->layer_acc);
   ctx->launches = 0;
+  return NHANS_OK;
+}
+
+int nhans_profile_get_layer(nhans_ctx* ctx, int net, int layer, double* stats) {
+  if (!ctx || !stats || net < 0 || net > 1 || layer < 0 || layer >= 64) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  prof_collect(ctx);
+  for (int i = 0; i < 4; ++i) stats[i] = ctx->layer_acc[net * 64 + layer][i];
   return NHANS_OK;
 }
 

@@ -9,9 +9,13 @@
 //                           128-byte swizzle, mbarrier complete_tx, multi-stage ring
 //   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, 4 x K = 16 per k-block,
 //                           accumulators in TMEM (2 x 256 columns, double buffered against the epilogue)
-//   warps 2-5 epilogue      tcgen05.ld -> + per-utterance conditioning bias + time / frequency embedding
-//                           tables + scaled identity residual / rank-1 transform -> ReLU -> fp16 store
-//                           into the consumer's padded grid (or fp32 + centre frame for the head)
+//   warps 2-9 epilogue      two warps per TMEM lane quarter, alternating 32-column chunks:
+//                           tcgen05.ld (thread = row) -> shared-memory transpose (warp-private, 32 rows x 32
+//                           columns) -> 8 lanes per row x 4 channels each, so that every table load, the
+//                           residual load and the fp16 store are coalesced; + per-utterance conditioning
+//                           bias + time / frequency embedding tables + scaled identity residual / rank-1
+//                           transform -> ReLU -> fp16 into the consumer's padded grid (or fp32 + centre
+//                           frame for the head)
 //
 // The epilogue is the fusion of blocks.py:104-108 (batch-norm), main.py:166,172 (conditioning adds),
 // main.py:184-186 (residual add, ReLU) folded as in SURVEY.md App. A.6.
@@ -24,6 +28,10 @@ namespace {
 
 constexpr int kABytes = 128 * 128;        // 128 rows x 64 fp16
 constexpr int kCtrlBytes = 4096;
+constexpr int kStagePitch = 36;           // floats per staged row (32 + 4: conflict-free 16-byte accesses)
+constexpr int kEpiWarps = 8;
+constexpr int kEpiWarpBytes = 32 * kStagePitch * 4 + 32 * 5 * 4;   // staging + per-row metadata of one warp
+constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
 constexpr int kMaxKb = 384;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -68,7 +76,7 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&ctrl->tmem_full[a], 1);
-      ptx::mbar_init(&ctrl->tmem_empty[a], 128);
+      ptx::mbar_init(&ctrl->tmem_empty[a], kEpiWarps * 32);
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -131,127 +139,160 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const EpiDev& e = p.epi;
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;
+    const int half = (warp - 2) >> 2;         // which of the two warps of the quarter: even / odd 32-column chunks
     const int hw = p.Hq * p.Wq;
+    uint8_t* epi_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + (warp - 2) * kEpiWarpBytes;
+    float* stage = reinterpret_cast<float*>(epi_base);
+    int* m_pix = reinterpret_cast<int*>(epi_base + 32 * kStagePitch * 4);        // [32] output pixel, -1 = skip
+    int* m_ho = m_pix + 32;
+    int* m_wo = m_ho + 32;
+    int* m_utt = m_wo + 32;
+    float* m_raw = reinterpret_cast<float*>(m_utt + 32);
+    const int sub = lane >> 3;                // row within a group of 4
+    const int c4 = (lane & 7) * 4;            // 4 channels per lane
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * 128;
       const int n0 = (tile % n_tiles) * p.BN;
-      const int m = m0 + row;
-      bool valid = m < p.M;
-      int unit = 0, ho = 0, wo = 0;
-      if (valid) {
-        unit = m / hw;
-        const int rem = m - unit * hw;
-        ho = rem / p.Wq;
-        wo = rem - ho * p.Wq;
-        valid = (ho < p.Ho) && (wo < p.Wo);
+      if (p.debug_skip_epilogue) {
+        ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+        continue;
       }
-      const float* bias_row = e.bias;
-      const float* t_row = nullptr;
-      const float* f_row = nullptr;
-      const __half* res_row = nullptr;
-      const float* raw_row = nullptr;
-      float rawv = 0.f;
-      __half* out_row = nullptr;
-      float* outf_row = nullptr;
-      if (valid) {
-        const int utt = p.units.utt ? p.units.utt[unit] : 0;
-        bias_row = e.bias + (size_t)utt * e.bias_stride;
-        if (e.ttab) t_row = e.ttab + (size_t)ho * p.N;
-        if (e.ftab) f_row = e.ftab + (size_t)wo * p.N;
-        if (e.res) res_row = e.res + (size_t)m * e.res_C;
-        if (e.r1_vec) {
-          const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
-          if (frame >= p.units.lo[unit] && frame < p.units.hi[unit])
-            rawv = e.raw[(size_t)frame * 201 + wo * e.r1_sw];
+      {
+        // per-row metadata, computed by the thread that owns the row in TMEM
+        const int m = m0 + q * 32 + lane;
+        bool valid = m < p.M;
+        int unit = 0, ho = 0, wo = 0;
+        if (valid) {
+          unit = m / hw;
+          const int rem = m - unit * hw;
+          ho = rem / p.Wq;
+          wo = rem - ho * p.Wq;
+          valid = (ho < p.Ho) && (wo < p.Wo);
         }
-        if (e.head) {
-          raw_row = e.raw + (size_t)p.units.frame[unit] * 201;
-          outf_row = e.out_f32 + (size_t)unit * 201;
-        } else {
-          long long pix;
-          if (e.o_mode == 1) {
-            pix = ((long long)unit * e.o_W + wo) * e.o_H + ho;
+        int pix = -1, utt = 0;
+        float rawv = 0.f;
+        if (valid) {
+          utt = p.units.utt ? p.units.utt[unit] : 0;
+          if (e.r1_vec) {
+            const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
+            if (frame >= p.units.lo[unit] && frame < p.units.hi[unit]) rawv = e.raw[(size_t)frame * 201 + wo * e.r1_sw];
+          }
+          if (e.head) {
+            pix = unit;
+            utt = p.units.frame[unit];       // head: the centre frame row replaces the utterance index
+          } else if (e.o_mode == 1) {
+            pix = (unit * e.o_W + wo) * e.o_H + ho;
           } else {
             const int y = ho + e.o_oy, x = wo + e.o_ox;
             const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
-            pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw);
+            pix = (int)(plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw));
           }
-          out_row = e.out + pix * e.out_C;
         }
+        m_pix[lane] = pix; m_ho[lane] = ho; m_wo[lane] = wo; m_utt[lane] = utt; m_raw[lane] = rawv;
       }
-
+      __syncwarp();
+      int pixs[8];
+      float4 fb[8], ft[8], ff[8];
+      uint2 fx[8];
+      // Issues every global load of one 32-column chunk (read-only path); called before the accumulator
+      // is awaited so that the memory latency hides behind the MMA main loop.
+      auto issue_loads = [&](int c0) {
+        const int col = n0 + c0 + c4;
+        const bool lane_ok = c4 < p.BN - c0 && !e.head;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int r = g * 4 + sub;
+          pixs[g] = m_pix[r];
+          const bool ok = lane_ok && pixs[g] >= 0;
+          fb[g] = ok ? __ldg(reinterpret_cast<const float4*>(e.bias + (size_t)m_utt[r] * e.bias_stride + col)) : zero4;
+          ft[g] = (ok && e.ttab) ? __ldg(reinterpret_cast<const float4*>(e.ttab + (size_t)m_ho[r] * p.N + col)) : zero4;
+          ff[g] = (ok && e.ftab) ? __ldg(reinterpret_cast<const float4*>(e.ftab + (size_t)m_wo[r] * p.N + col)) : zero4;
+          fx[g] = (ok && e.res) ? __ldg(reinterpret_cast<const uint2*>(e.res + (size_t)(m0 + q * 32 + r) * e.res_C + col)) : make_uint2(0u, 0u);
+        }
+      };
+      int c0 = half * 32;
+      if (c0 < p.BN) issue_loads(c0);
       ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_addr + c0, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          const int col = n0 + c0;
-          float f[16];
+      for (; c0 < p.BN; c0 += 64) {
+        const int width = min(32, p.BN - c0);
+        // phase 1: TMEM (thread = row) -> staging
+        if (width == 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(t_addr + c0, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_row + col + i);
-            f[i] = __uint_as_float(v[i]) + b.x;
-            f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
-            f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
-            f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
-          }
-          if (t_row) {
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(stage + lane * kStagePitch + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          uint32_t v[16];
+          ptx::tmem_ld16(t_addr + c0, v);
+          ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(t_row + col + i);
-              f[i] += t.x; f[i + 1] += t.y; f[i + 2] += t.z; f[i + 3] += t.w;
-            }
-          }
-          if (f_row) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(f_row + col + i);
-              f[i] += t.x; f[i + 1] += t.y; f[i + 2] += t.z; f[i + 3] += t.w;
-            }
-          }
-          if (res_row) {
-            const uint4 r0 = *reinterpret_cast<const uint4*>(res_row + col);
-            const uint4 r1 = *reinterpret_cast<const uint4*>(res_row + col + 8);
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
-              f[2 * i] = fmaf(e.res_scale[col + 2 * i], x.x, f[2 * i]);
-              f[2 * i + 1] = fmaf(e.res_scale[col + 2 * i + 1], x.y, f[2 * i + 1]);
-            }
-          }
-          if (e.r1_vec) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaf(e.r1_vec[col + i], rawv, f[i]);
-          }
-          if (e.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stage + lane * kStagePitch + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        __syncwarp();
+        // phase 2: 8 lanes per row, 4 channels per lane
+        if (c4 < width) {
+          const int col = n0 + c0 + c4;
           if (e.head) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (col + i < 201) outf_row[col + i] = f[i] + raw_row[col + i];
+            for (int g = 0; g < 8; ++g) {
+              const int r = g * 4 + sub;
+              const int pix = m_pix[r];
+              if (pix < 0) continue;
+              const float4 f = *reinterpret_cast<const float4*>(stage + r * kStagePitch + c4);
+              const float* raw_row = e.raw + (size_t)m_utt[r] * 201;
+              float* o = e.out_f32 + (size_t)pix * 201;
+              if (col < 201) o[col] = f.x + b.x + raw_row[col];
+              if (col + 1 < 201) o[col + 1] = f.y + b.y + raw_row[col + 1];
+              if (col + 2 < 201) o[col + 2] = f.z + b.z + raw_row[col + 2];
+              if (col + 3 < 201) o[col + 3] = f.w + b.w + raw_row[col + 3];
+            }
           } else {
-            uint4 o0, o1;
-            o0.x = pack_half2(f[0], f[1]);   o0.y = pack_half2(f[2], f[3]);
-            o0.z = pack_half2(f[4], f[5]);   o0.w = pack_half2(f[6], f[7]);
-            o1.x = pack_half2(f[8], f[9]);   o1.y = pack_half2(f[10], f[11]);
-            o1.z = pack_half2(f[12], f[13]); o1.w = pack_half2(f[14], f[15]);
-            *reinterpret_cast<uint4*>(out_row + col) = o0;
-            *reinterpret_cast<uint4*>(out_row + col + 8) = o1;
+            const float4 rs = e.res ? __ldg(reinterpret_cast<const float4*>(e.res_scale + col)) : zero4;
+            const float4 r1 = e.r1_vec ? __ldg(reinterpret_cast<const float4*>(e.r1_vec + col)) : zero4;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (pixs[g] < 0) continue;
+              const int r = g * 4 + sub;
+              float4 f = *reinterpret_cast<const float4*>(stage + r * kStagePitch + c4);
+              f.x += fb[g].x + ft[g].x + ff[g].x; f.y += fb[g].y + ft[g].y + ff[g].y;
+              f.z += fb[g].z + ft[g].z + ff[g].z; f.w += fb[g].w + ft[g].w + ff[g].w;
+              const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&fx[g].x));
+              const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&fx[g].y));
+              f.x = fmaf(rs.x, x0.x, f.x); f.y = fmaf(rs.y, x0.y, f.y);
+              f.z = fmaf(rs.z, x1.x, f.z); f.w = fmaf(rs.w, x1.y, f.w);
+              if (e.r1_vec) {
+                const float rawv = m_raw[r];
+                f.x = fmaf(r1.x, rawv, f.x); f.y = fmaf(r1.y, rawv, f.y);
+                f.z = fmaf(r1.z, rawv, f.z); f.w = fmaf(r1.w, rawv, f.w);
+              }
+              if (e.relu) {
+                f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+              }
+              uint2 o;
+              o.x = pack_half2(f.x, f.y);
+              o.y = pack_half2(f.z, f.w);
+              *reinterpret_cast<uint2*>(e.out + (size_t)pixs[g] * e.out_C + col) = o;
+            }
           }
         }
+        __syncwarp();                         // staging is overwritten by the next chunk
+        if (c0 + 64 < p.BN) issue_loads(c0 + 64);
       }
+      __syncwarp();                           // metadata is overwritten by the next tile
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
     }
@@ -270,10 +311,10 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
 int gemm_smem_bytes(int BN, int* stages_out) {
   const int stage_bytes = kABytes + BN * 128;
-  int stages = (kSmemLimit - kCtrlBytes - 1024) / stage_bytes;
+  int stages = (kSmemLimit - kCtrlBytes - kEpiBytes - 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages_out) *stages_out = stages;
-  return stages * stage_bytes + kCtrlBytes + 1024;
+  return stages * stage_bytes + kCtrlBytes + kEpiBytes + 1024;
 }
 
 cudaError_t gemm_configure() {

@@ -54,6 +54,7 @@ struct GemmDev {
   UnitTable units;
   EpiDev epi;
   int* err_flag;
+  int debug_skip_epilogue;  // measurement aid: epilogue warps only release the accumulator
 };
 
 struct DirectDev {
@@ -66,7 +67,7 @@ struct DirectDev {
   EpiDev epi;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;     // TMA warp + MMA warp + 8 epilogue warps
 int gemm_smem_bytes(int BN, int* stages_out);
 cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,

@@ -220,6 +220,16 @@ class Engine:
         self._ck(self.lib.nhans_profile_get(self.h, kind, _ptr(st)))
         return dict(launches=int(st[0]), ms=float(st[1]), flops=float(st[2]), bytes=float(st[3]))
 
+    def profile_layers(self, net=0):
+        """Per tensor-core layer: name, launches, ms, algorithmic TFLOP/s."""
+        out = []
+        for i, g in enumerate(self.plan(net)["gemm"]):
+            st = np.zeros(4, np.float64)
+            self._ck(self.lib.nhans_profile_get_layer(self.h, net, i, _ptr(st)))
+            out.append(dict(name=g["name"], launches=int(st[0]), ms=float(st[1]),
+                            tflops=float(st[2] / st[1] / 1e9) if st[1] > 0 else 0.0, K=g["K"], N=g["N"]))
+        return out
+
     def plan(self, net=0):
         return json.loads(self.lib.nhans_plan_json(self.h, net).decode())
 

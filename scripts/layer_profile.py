@@ -1,0 +1,39 @@
+"""Per-layer timing of the tensor-core layers on a GPU box (CUDA events around every launch).
+   python scripts/layer_profile.py [utts] [seconds]   -> table + gpurun_out/layers.json"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nhans_b200 import synth, weights as W  # noqa: E402
+from nhans_b200.engine import Engine, pack  # noqa: E402
+
+utts = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+secs = float(sys.argv[2]) if len(sys.argv) > 2 else 4.0
+eng = Engine(0, 0)
+eng.load_weights(W.seeded_init(0, 0))
+base = [synth.mixture(secs, u) for u in range(8)]
+negs = [synth.noise_clip(u) for u in range(8)]
+mix, mo = pack([base[u % 8] for u in range(utts)])
+neg, no = pack([negs[u % 8] for u in range(utts)])
+eng.upload(mix, mo, None, None, neg, no)
+eng.run(); eng.sync()
+eng.profile_reset(); eng.profile(True)
+eng.event_record(0)
+for _ in range(2):
+    eng.run()
+eng.event_record(1)
+eng.sync()
+ms = eng.event_elapsed_ms(0, 1)
+layers = eng.profile_layers(0)
+tot = sum(l["ms"] for l in layers)
+print("skip_epilogue=%s  %d x %.0f s: %.1f ms/run -> %.1f audio-s/s" % (os.environ.get("NHANS_DEBUG_SKIP_EPILOGUE", "0"), utts, secs, ms / 2, utts * secs / (ms / 2e3)))
+for l in layers:
+    print("%-22s K=%5d N=%3d  %8.2f ms  %5.1f%%  %7.1f TFLOP/s" % (l["name"], l["K"], l["N"], l["ms"] / 2, 100 * l["ms"] / tot, l["tflops"]))
+st = eng.profile_get(0)
+print("all GEMM layers: %.1f ms, %.1f TFLOP/s;  direct conv %.1f ms" % (st["ms"] / 2, st["flops"] / st["ms"] / 1e9, eng.profile_get(3)["ms"] / 2))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(layers, open(os.path.join(ROOT, "gpurun_out", "layers_skip%s.json" % os.environ.get("NHANS_DEBUG_SKIP_EPILOGUE", "0")), "w"))
