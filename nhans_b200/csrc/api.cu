@@ -48,7 +48,7 @@ struct DBuf {
 
 struct GemmLayerDev {
   __half* w = nullptr;
-  KBlockDev* kb = nullptr;
+  KGroupDev* groups = nullptr;
   float *bias = nullptr, *ttab = nullptr, *ftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
   CUtensorMap mapA0, mapA1, mapB;
 };
@@ -106,6 +106,7 @@ struct nhans_ctx {
   std::vector<cudaEvent_t> ev_pool;
   double prof_acc[5][4] = {};
   int debug_skip_epilogue = 0;
+  int desc_mode = 0;
   double layer_acc[128][4] = {};
   double launches = 0;              // every kernel launched by this context (counted even when not profiling)
 };
@@ -192,9 +193,15 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
       CK(cudaMemcpyAsync(p, L.w.data(), L.w.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
       D.w = reinterpret_cast<__half*>(p);
     }
-    std::vector<KBlockDev> kb(L.kb.size());
-    for (size_t j = 0; j < kb.size(); ++j) kb[j] = {L.kb[j].row_off, L.kb[j].map, L.kb[j].col};
-    if ((rc = upload(ctx, net, kb, &D.kb))) return rc;
+    std::vector<KGroupDev> groups(L.groups.size());
+    for (size_t j = 0; j < groups.size(); ++j) {
+      const KGroup& g = L.groups[j];
+      KGroupDev d;
+      d.row_off = g.row_off; d.map = g.map; d.col = g.col; d.ntaps = g.ntaps; d.pad_ = 0;
+      for (int t = 0; t < 4; ++t) { d.shift[t] = g.shift[t]; d.bk[t] = g.bk[t]; }
+      groups[j] = d;
+    }
+    if ((rc = upload(ctx, net, groups, &D.groups))) return rc;
     if ((rc = upload(ctx, net, L.epi.bias, &D.bias))) return rc;
     if ((rc = upload(ctx, net, L.epi.ttab, &D.ttab))) return rc;
     if ((rc = upload(ctx, net, L.epi.ftab, &D.ftab))) return rc;
@@ -206,7 +213,7 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
       const Grid& g = P.bufs[buf];
       long long elems = (long long)g.pixels * g.C;
       if (elems % rowlen) return fail(ctx, NHANS_ERR_STATE, "buffer size not a multiple of the TMA row length");
-      if ((rc = make_map(ctx, a == 0 ? &D.mapA0 : &D.mapA1, net.bufs[buf], rowlen, elems / rowlen, 128))) return rc;
+      if ((rc = make_map(ctx, a == 0 ? &D.mapA0 : &D.mapA1, net.bufs[buf], rowlen, elems / rowlen, 136))) return rc;
     }
     if ((rc = make_map(ctx, &D.mapB, D.w, L.K, L.N, L.BN))) return rc;
   }
@@ -330,14 +337,14 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     memset(&g, 0, sizeof g);
     long long M = (long long)units * L.Hq * L.Wq;
     if (M > 0x7fffffffLL) return fail(ctx, NHANS_ERR_ARG, "too many rows in one pass");
-    g.M = (int)M; g.N = L.N; g.BN = L.BN; g.num_kb = (int)L.kb.size(); g.kb = D.kb;
+    g.M = (int)M; g.N = L.N; g.BN = L.BN; g.num_kb = (int)L.kb.size(); g.num_groups = (int)L.groups.size(); g.groups = D.groups;
     g.Hq = L.Hq; g.Wq = L.Wq; g.Ho = L.Ho; g.Wo = L.Wo;
     g.units = ut;
     g.epi = make_epi(net, L.epi, L.out, D.bias, D.ttab, D.ftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);
     g.err_flag = ctx->err_flag_dev;
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
     ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0, (&net == &ctx->tower ? 64 : 0) + (int)i);
-    CK(launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, g));
+    CK(launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, g, ctx->desc_mode));
   }
   return 0;
 }
@@ -441,6 +448,7 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   if (win_capacity > 0) ctx->win_cap = win_capacity;
   if (row_capacity > 0) ctx->row_cap = row_capacity;
   if (const char* dbg = getenv("NHANS_DEBUG_SKIP_EPILOGUE")) ctx->debug_skip_epilogue = atoi(dbg);
+  if (const char* dbg = getenv("NHANS_DESC_MODE")) ctx->desc_mode = atoi(dbg);
   ctx->n_sm = prop.multiProcessorCount;
   auto bail = [&](const std::string& m) { g_create_error = m; return NHANS_ERR_CUDA; };
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));

@@ -39,17 +39,27 @@ struct EpiDev {
   float* out_f32;
 };
 
-struct KBlockDev {
+struct KGroupDev {            // plan.h KGroup
   int32_t row_off;
-  int16_t map;
-  int16_t col;
+  int16_t map, col, ntaps, pad_;
+  int16_t shift[4];
+  int32_t bk[4];
+};
+
+struct GemmCfg {              // chosen by the host per layer shape
+  int mt;                     // 128-row sub-tiles per CTA tile (256 / BN)
+  int na, nb;                 // A slab ring / B tile ring depth
+  int resident;               // all k-blocks of B fit in the ring: load once
+  int desc_mode;              // 1: set the descriptor base-offset field for row-shifted slabs
+  int il;                     // sub-tiles whose MMAs are interleaved (1, 2 or 4; divides mt, <= na)
 };
 
 struct GemmDev {
   int M;                    // compute rows = units * Hq * Wq
   int N, BN;
-  int num_kb;
-  const KBlockDev* kb;
+  int num_kb;               // k-blocks (64 wide) of the packed weights
+  int num_groups;
+  const KGroupDev* groups;
   int Hq, Wq, Ho, Wo;
   UnitTable units;
   EpiDev epi;
@@ -67,11 +77,11 @@ struct DirectDev {
   EpiDev epi;
 };
 
-constexpr int kGemmThreads = 320;     // TMA warp + MMA warp + 8 epilogue warps
-int gemm_smem_bytes(int BN, int* stages_out);
+constexpr int kGemmThreads = 224;     // A producer, B producer, MMA issuer, 4 epilogue warps
+int gemm_smem_bytes(int BN, int num_kb, GemmCfg* cfg);
 cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
-                        const CUtensorMap& mapB, const GemmDev& p);
+                        const CUtensorMap& mapB, const GemmDev& p, int desc_mode);
 cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p);
 
 // bias_utt[u][j] = emb_a[u] . Pa[:, j] + emb_b[u] . Pb[:, j] + c[j]

@@ -304,6 +304,7 @@ struct Builder {
       L.epi = e1;
       L.out = h;
       L.macs_per_unit = macs1;
+      build_groups(&L);
       plan.gemm.push_back(std::move(L));
     }
 
@@ -341,6 +342,7 @@ struct Builder {
     site_epilogue(b.scope + "_conv2", C, g.Ho, g.Wo, bnA.s, constant, &e2);
     L.epi = e2;
     L.out = y;
+    build_groups(&L);
     plan.gemm.push_back(std::move(L));
   }
 };
@@ -401,6 +403,29 @@ void build_blocks(Builder* B, const std::vector<BlockSpec>& blocks, int H, int W
 
 }  // namespace
 
+void build_groups(GemmLayer* L) {
+  L->groups.clear();
+  const int n = (int)L->kb.size();
+  std::vector<char> used(n, 0);
+  for (int a = 0; a < n; ++a) {
+    if (used[a]) continue;
+    KGroup g{};
+    g.row_off = L->kb[a].row_off; g.map = L->kb[a].map; g.col = L->kb[a].col;
+    g.ntaps = 0;
+    // taps of the same source / channel chunk whose rows lie within 7 rows above the first one
+    for (int b = a; b < n && g.ntaps < 4; ++b) {
+      if (used[b] || L->kb[b].map != g.map || L->kb[b].col != g.col) continue;
+      const int64_t d = (int64_t)L->kb[b].row_off - g.row_off;
+      if (d < 0 || d > 7) continue;
+      g.shift[g.ntaps] = (int16_t)d;
+      g.bk[g.ntaps] = b;
+      g.ntaps++;
+      used[b] = 1;
+    }
+    L->groups.push_back(g);
+  }
+}
+
 static std::string grid_json(const Grid& g) {
   char b[512];
   snprintf(b, sizeof b,
@@ -421,9 +446,9 @@ std::string plan_to_json(const NetPlan& p) {
     char b[512];
     snprintf(b, sizeof b,
              "%s{\"name\":\"%s\",\"Hq\":%d,\"Wq\":%d,\"Ho\":%d,\"Wo\":%d,\"N\":%d,\"BN\":%d,\"K\":%d,\"a_buf\":[%d,%d],"
-             "\"res_buf\":%d,\"cond_off\":%d,\"macs\":%.1f,\"out\":",
+             "\"res_buf\":%d,\"cond_off\":%d,\"groups\":%d,\"macs\":%.1f,\"out\":",
              i ? "," : "", L.name.c_str(), L.Hq, L.Wq, L.Ho, L.Wo, L.N, L.BN, L.K, L.a_buf[0], L.a_buf[1], L.epi.res_buf,
-             L.epi.cond_off, L.macs_per_unit);
+             L.epi.cond_off, (int)L.groups.size(), L.macs_per_unit);
     s += b + grid_json(L.out) + "}";
   }
   s += "]}";
@@ -470,6 +495,7 @@ NetPlan build_main_plan(const WeightMap& w, int variant, int capacity) {
     o.buf = B.new_buf(o);
     L.out = o;
     L.macs_per_unit = 26.0 * 2560 * 512;
+    build_groups(&L);
     P.gemm.push_back(std::move(L));
   }
   // flatten (f * 512 + c) -> last_dense -> + mixed_central (main.py:236-242)
@@ -490,6 +516,7 @@ NetPlan build_main_plan(const WeightMap& w, int variant, int capacity) {
     L.epi.relu = 0;
     L.epi.head = 1;
     L.macs_per_unit = 13312.0 * kBins;
+    build_groups(&L);
     P.gemm.push_back(std::move(L));
   }
   return P;

@@ -61,6 +61,19 @@ struct KBlock {                   // one 64-wide k-block of a GemmLayer
   int16_t col;                    // first channel
 };
 
+// A group of up to 4 k-blocks whose A rows differ only by a small row shift (the kw taps of one kernel row
+// and one 64-channel chunk): the engine loads ONE slab of 128 + 8 rows and feeds every tap from it through
+// row-shifted UMMA descriptors, so A is fetched from L2 once per kernel row instead of once per tap.
+struct KGroup {
+  int32_t row_off;                // row offset of shift 0
+  int16_t map;                    // 0: A0, 1: A1
+  int16_t col;                    // first channel
+  int16_t ntaps;
+  int16_t pad_;
+  int16_t shift[4];               // extra rows of tap t (0..7)
+  int32_t bk[4];                  // k-block index of tap t in the packed weights
+};
+
 struct Epilogue {
   // v = acc + bias[utt * bias_stride + n] + ttab[ho][n] + ftab[wo][n]
   //       + res_scale[n] * res[m][n] + r1_vec[n] * raw(n, ho, wo);  v = relu ? max(v, 0) : v
@@ -85,6 +98,7 @@ struct GemmLayer {
   int N = 0, BN = 0;                      // N padded to a multiple of 16; BN = columns per CTA tile
   int K = 0;                              // 64 * kb.size()
   std::vector<KBlock> kb;
+  std::vector<KGroup> groups;             // kb regrouped for slab reuse (same k-blocks, same order of B)
   std::vector<uint16_t> w;                // fp16 bits, [N][K] (K contiguous)
   Epilogue epi;
   Grid out;                               // out.buf < 0 for the head
@@ -130,6 +144,9 @@ NetPlan build_tower_plan(const WeightMap& w, int capacity);
 
 // TF 'SAME' padding: out = ceil(n / s), pad = max((out - 1) s + k - n, 0), before = pad / 2
 void same_pads(int n, int k, int s, int* out, int* before, int* after);
+
+// Regroups L->kb into L->groups (call once the k-block list is complete).
+void build_groups(GemmLayer* L);
 
 // JSON description of a plan (geometry only, no weights) for tests and DESIGN tables.
 std::string plan_to_json(const NetPlan& p);

@@ -20,6 +20,20 @@ __device__ __forceinline__ uint64_t globaltimer() {
   return t;
 }
 
+// One lane of a converged warp (the CUTLASS elect_one_sync idiom): single-thread async instructions
+// (TMA, tcgen05.mma, tcgen05.commit) are issued under this predicate from warp-uniform control flow.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -88,8 +102,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 // K-major, 128-byte swizzle operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1
 // (Blackwell), layout type 2 (SWIZZLE_128B).  See cute/arch/mma_sm100_desc.hpp SmemDescriptor.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// `mode` 1 additionally sets the 3-bit base-offset field (bits 49-51) to (address >> 7) & 7 for operands that
+// start inside a 1024-byte swizzle atom (row-shifted A slabs).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, int mode) {
   uint64_t d = 0;
+  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
   d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
@@ -113,6 +130,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_commit_raw(uint64_t* bar) { umma_commit(bar); }
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (32 * (warp % 4) + i).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -122,16 +122,17 @@ void run_net(Net& net, int units_n, const Units& units, const float* raw, const 
       const int ho = rem / L.Wq, wo = rem % L.Wq;
       if (ho >= L.Ho || wo >= L.Wo) continue;
       std::vector<float> acc(L.N, 0.f);
-      for (size_t j = 0; j < L.kb.size(); ++j) {
-        const KBlock& kb = L.kb[j];
-        const long long row = m + kb.row_off;
-        if (row < 0 || row >= rows[kb.map]) continue;          // TMA out-of-bounds rows read as zero
-        const float* a = &net.bufs[L.a_buf[kb.map]][(size_t)row * L.a_rowlen[kb.map] + kb.col];
-        for (int kk = 0; kk < kTileK; ++kk) {
-          const float av = a[kk];
-          if (av == 0.f) continue;
-          const float* w = &wt[(size_t)(j * kTileK + kk) * L.N];
-          for (int n = 0; n < L.N; ++n) acc[n] += av * w[n];
+      for (const KGroup& g : L.groups) {
+        for (int t = 0; t < g.ntaps; ++t) {
+          const long long row = m + g.row_off + g.shift[t];
+          if (row < 0 || row >= rows[g.map]) continue;          // TMA out-of-bounds rows read as zero
+          const float* a = &net.bufs[L.a_buf[g.map]][(size_t)row * L.a_rowlen[g.map] + g.col];
+          for (int kk = 0; kk < kTileK; ++kk) {
+            const float av = a[kk];
+            if (av == 0.f) continue;
+            const float* w = &wt[(size_t)(g.bk[t] * kTileK + kk) * L.N];
+            for (int n = 0; n < L.N; ++n) acc[n] += av * w[n];
+          }
         }
       }
       epilogue(c, L.epi, L.out, L.N, unit, ho, wo, m, acc.data(), net.bufs);
