@@ -123,6 +123,9 @@ int nhans_profile_get_layer(nhans_ctx* ctx, int net, int layer, double* stats);
 const char* nhans_plan_json(nhans_ctx* ctx, int net);
 /* Copy activation buffer `buf` of net (fp16 bits) to the host: n_elems must not exceed its size. */
 int nhans_debug_read_buffer(nhans_ctx* ctx, int net, int buf, uint16_t* out, int64_t n_elems);
+/* Debug: accumulated wait cycles of one tensor-core layer (needs NHANS_DEBUG_STATS=1 at create time):
+ * {MMA waits accumulator free, MMA waits A, MMA waits B, epilogue waits accumulator ready, MMA warp total, ...}. */
+int nhans_debug_layer_stats(nhans_ctx* ctx, int net, int layer, uint64_t* out8);
 int nhans_device_info(nhans_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes);
 
 #ifdef __cplusplus

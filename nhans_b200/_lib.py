@@ -16,7 +16,7 @@ SYMBOLS = [
     "nhans_upload", "nhans_run", "nhans_download", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
     "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset",
     "nhans_profile_get_layer", "nhans_plan_json",
-    "nhans_debug_read_buffer", "nhans_device_info",
+    "nhans_debug_read_buffer", "nhans_debug_layer_stats", "nhans_device_info",
 ]
 
 

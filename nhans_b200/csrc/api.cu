@@ -49,7 +49,7 @@ struct DBuf {
 struct GemmLayerDev {
   __half* w = nullptr;
   KGroupDev* groups = nullptr;
-  float *bias = nullptr, *ttab = nullptr, *ftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
+  float *bias = nullptr, *tftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
   CUtensorMap mapA0, mapA1, mapB;
 };
 
@@ -57,7 +57,7 @@ struct NetDev {
   NetPlan plan;
   std::vector<__half*> bufs;
   std::vector<GemmLayerDev> layers;
-  float *first_w = nullptr, *first_bias = nullptr, *first_ttab = nullptr, *first_ftab = nullptr;
+  float *first_w = nullptr, *first_bias = nullptr, *first_tftab = nullptr;
   float *Pa = nullptr, *Pb = nullptr, *c = nullptr;
   int *u_frame = nullptr, *u_lo = nullptr, *u_hi = nullptr, *u_utt = nullptr;
   std::vector<void*> allocs;
@@ -106,6 +106,7 @@ struct nhans_ctx {
   std::vector<cudaEvent_t> ev_pool;
   double prof_acc[5][4] = {};
   int debug_skip_epilogue = 0;
+  unsigned long long* debug_stats = nullptr;   // [128][8] per-layer wait-cycle counters (NHANS_DEBUG_STATS=1)
   int desc_mode = 0;
   double layer_acc[128][4] = {};
   double launches = 0;              // every kernel launched by this context (counted even when not profiling)
@@ -177,8 +178,7 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
   int rc;
   if ((rc = upload(ctx, net, P.first.w, &net.first_w))) return rc;
   if ((rc = upload(ctx, net, P.first.epi.bias, &net.first_bias))) return rc;
-  if ((rc = upload(ctx, net, P.first.epi.ttab, &net.first_ttab))) return rc;
-  if ((rc = upload(ctx, net, P.first.epi.ftab, &net.first_ftab))) return rc;
+  if ((rc = upload(ctx, net, P.first.epi.tftab, &net.first_tftab))) return rc;
   if ((rc = upload(ctx, net, P.cond.Pa, &net.Pa))) return rc;
   if ((rc = upload(ctx, net, P.cond.Pb, &net.Pb))) return rc;
   if ((rc = upload(ctx, net, P.cond.c, &net.c))) return rc;
@@ -203,8 +203,7 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
     }
     if ((rc = upload(ctx, net, groups, &D.groups))) return rc;
     if ((rc = upload(ctx, net, L.epi.bias, &D.bias))) return rc;
-    if ((rc = upload(ctx, net, L.epi.ttab, &D.ttab))) return rc;
-    if ((rc = upload(ctx, net, L.epi.ftab, &D.ftab))) return rc;
+    if ((rc = upload(ctx, net, L.epi.tftab, &D.tftab))) return rc;
     if ((rc = upload(ctx, net, L.epi.res_scale, &D.res_scale))) return rc;
     if ((rc = upload(ctx, net, L.epi.r1_vec, &D.r1_vec))) return rc;
     for (int a = 0; a < 2; ++a) {
@@ -287,8 +286,8 @@ void fill_out(EpiDev& e, const NetDev& net, const Grid& g) {
   e.o_plane = g.plane_stride;
 }
 
-EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const float* bias_const, const float* ttab,
-                const float* ftab, const float* res_scale, const float* r1_vec, const float* raw, const float* cond_table,
+EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const float* bias_const, const float* tftab,
+                const float* res_scale, const float* r1_vec, const float* raw, const float* cond_table,
                 float* out_f32) {
   EpiDev e;
   memset(&e, 0, sizeof e);
@@ -299,7 +298,7 @@ EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const flo
     e.bias = bias_const;
     e.bias_stride = 0;
   }
-  e.ttab = ttab; e.ftab = ftab;
+  e.tftab = tftab;
   if (E.res_buf >= 0) {
     e.res = net.bufs[E.res_buf];
     e.res_C = net.plan.bufs[E.res_buf].C;
@@ -326,7 +325,7 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     d.Hin = D.Hin; d.Win = D.Win; d.raw_oh = D.raw_oh; d.Ho = D.Ho; d.Wo = D.Wo; d.N = D.N;
     d.w = net.first_w;
     d.units_tab = ut;
-    d.epi = make_epi(net, D.epi, D.out, net.first_bias, net.first_ttab, net.first_ftab, nullptr, nullptr, raw, cond_table, nullptr);
+    d.epi = make_epi(net, D.epi, D.out, net.first_bias, net.first_tftab, nullptr, nullptr, raw, cond_table, nullptr);
     ProfScope ps(ctx, 3, 2.0 * D.macs_per_unit * units, 0);
     CK(launch_direct_conv(ctx->stream, d));
   }
@@ -340,9 +339,10 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.M = (int)M; g.N = L.N; g.BN = L.BN; g.num_kb = (int)L.kb.size(); g.num_groups = (int)L.groups.size(); g.groups = D.groups;
     g.Hq = L.Hq; g.Wq = L.Wq; g.Ho = L.Ho; g.Wo = L.Wo;
     g.units = ut;
-    g.epi = make_epi(net, L.epi, L.out, D.bias, D.ttab, D.ftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);
+    g.epi = make_epi(net, L.epi, L.out, D.bias, D.tftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);
     g.err_flag = ctx->err_flag_dev;
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
+    g.debug_stats = ctx->debug_stats ? ctx->debug_stats + 8 * ((&net == &ctx->tower ? 64 : 0) + (int)i) : nullptr;
     ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0, (&net == &ctx->tower ? 64 : 0) + (int)i);
     CK(launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, g, ctx->desc_mode));
   }
@@ -449,6 +449,9 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   if (row_capacity > 0) ctx->row_cap = row_capacity;
   if (const char* dbg = getenv("NHANS_DEBUG_SKIP_EPILOGUE")) ctx->debug_skip_epilogue = atoi(dbg);
   if (const char* dbg = getenv("NHANS_DESC_MODE")) ctx->desc_mode = atoi(dbg);
+  if (const char* dbg = getenv("NHANS_DEBUG_STATS")) {
+    if (atoi(dbg) && cudaMalloc((void**)&ctx->debug_stats, 128 * 8 * 8) == cudaSuccess) cudaMemset(ctx->debug_stats, 0, 128 * 8 * 8);
+  }
   ctx->n_sm = prop.multiProcessorCount;
   auto bail = [&](const std::string& m) { g_create_error = m; return NHANS_ERR_CUDA; };
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
@@ -889,6 +892,13 @@ int nhans_profile_reset(nhans_ctx* ctx) {
   memset(ctx->layer_acc, 0, sizeof ctx->layer_acc);
   ctx->launches = 0;
   return NHANS_OK;
+}
+
+int nhans_debug_layer_stats(nhans_ctx* ctx, int net, int layer, uint64_t* out8) {
+  if (!ctx || !out8 || !ctx->debug_stats || net < 0 || net > 1 || layer < 0 || layer >= 64) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  return cudaMemcpy(out8, ctx->debug_stats + 8 * (net * 64 + layer), 64, cudaMemcpyDeviceToHost) == cudaSuccess ? NHANS_OK : NHANS_ERR_CUDA;
 }
 
 int nhans_profile_get_layer(nhans_ctx* ctx, int net, int layer, double* stats) {

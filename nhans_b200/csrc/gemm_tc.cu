@@ -14,7 +14,7 @@
 //                           fit (K * BN * 2 B <= ring) the weights are loaded once and stay resident
 //   warp 2   MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, 4 x (K = 16) per tap,
 //                           fp32 accumulators in TMEM
-//   warps 3-6 epilogue      tcgen05.ld (thread = row) -> shared-memory transpose (warp-private 32 x 32) ->
+//   warps 3-10 epilogue     tcgen05.ld (thread = row) -> shared-memory transpose (warp-private 32 x 32) ->
 //                           8 lanes per row x 4 channels, so every table load, the residual load and the
 //                           fp16 store are coalesced; all global loads of a chunk are issued before the
 //                           accumulator is awaited.  + per-utterance conditioning bias + time / frequency
@@ -33,9 +33,8 @@ namespace {
 constexpr int kSlabRows = 136;                    // 128 + up to 7 rows of tap shift, multiple of 8
 constexpr int kSlabBytes = kSlabRows * 128;       // 17 KB, a multiple of the 1024-byte swizzle atom
 constexpr int kCtrlBytes = 8192;
-constexpr int kStagePitch = 36;                   // floats per staged row (32 + 4: conflict-free 16-byte accesses)
-constexpr int kEpiWarps = 4;
-constexpr int kEpiWarpBytes = 32 * kStagePitch * 4 + 32 * 5 * 4;   // staging + per-row metadata of one warp
+constexpr int kEpiWarps = 8;
+constexpr int kEpiWarpBytes = 32 * 64 + 32 * 16;                   // 32 x 16 fp32 transpose buffer + row metadata
 constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
 constexpr int kMaxGroups = 212;
 constexpr int kMaxA = 8, kMaxB = 16;
@@ -70,9 +69,11 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   const uint32_t b_step = (uint32_t)b_bytes >> 4;
   uint32_t aslot = 0, aphase = 0, bslot0 = 0, bphase0 = 0, it = 0;
   bool b_ready = false;                                             // resident weights have landed
+  long long w_tmem = 0, w_a = 0, w_b = 0;
+  const long long t_start = clock64();
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-    ptx::mbar_wait(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2);
+    ptx::mbar_wait_timed(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2, &w_tmem);
     ptx::tc_fence_after();
     for (int g = 0; g < num_groups; ++g) {
       const int ntaps = ctrl->groups[g].ntaps;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
         for (int ii = 0; ii < IL; ++ii) {
           uint32_t sl = aslot + ii, ph = aphase;
           if (sl >= (uint32_t)cfg.na) { sl -= cfg.na; ph ^= 1; }
-          ptx::mbar_wait(&ctrl->a_full[sl], ph, p.err_flag, 3);
+          ptx::mbar_wait_timed(&ctrl->a_full[sl], ph, p.err_flag, 3, &w_a);
           a_lo[ii] = a_base + sl * (kSlabBytes >> 4);
           d_tm[ii] = tmem_base + acc * 256 + (i0 + ii) * p.BN;
         }
@@ -90,7 +91,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
         for (int t = 0; t < ntaps; ++t) {
           if (cfg.resident) bslot = (uint32_t)ctrl->groups[g].bk[t];
           if ((i0 == 0 && !cfg.resident) || (cfg.resident && !b_ready))
-            ptx::mbar_wait(&ctrl->b_full[bslot], cfg.resident ? 0u : bphase, p.err_flag, 6);
+            ptx::mbar_wait_timed(&ctrl->b_full[bslot], cfg.resident ? 0u : bphase, p.err_flag, 6, &w_b);
           ptx::tc_fence_after();
           const uint32_t sh = (uint32_t)ctrl->groups[g].shift[t] * 8;
           const uint32_t b_lo = b_base + bslot * b_step;
@@ -120,6 +121,12 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
     b_ready = true;
     if (ptx::elect_one()) ptx::umma_commit(&ctrl->tmem_full[acc]);
     __syncwarp();
+  }
+  if (p.debug_stats && (threadIdx.x & 31) == 0) {
+    atomicAdd(p.debug_stats + 0, (unsigned long long)w_tmem);
+    atomicAdd(p.debug_stats + 1, (unsigned long long)w_a);
+    atomicAdd(p.debug_stats + 2, (unsigned long long)w_b);
+    atomicAdd(p.debug_stats + 4, (unsigned long long)(clock64() - t_start));
   }
 }
 
@@ -220,169 +227,175 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     else if (cfg.il == 2) mma_issuer<2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
     else mma_issuer<1>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
   } else {
-    // ===================== epilogue (warps 3..6) =====================
+    // ===================== epilogue (warps 3..10) =====================
+    // With ~225 KB of shared memory in use there is no L1 left: every table / residual read is an L2 round
+    // trip of a few thousand cycles under load, so the epilogue is latency bound.  Hence: two warps per TMEM
+    // lane quarter (alternating 16-column chunks), small chunks whose loads fit in registers twice, and the
+    // loads of chunk k+1 in flight while chunk k is transposed and stored.
     const EpiDev& e = p.epi;
+    const int ew = warp - 3;
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                 // which of the two warps of the quarter
     const int hw = p.Hq * p.Wq;
-    uint8_t* epi_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + (warp - 3) * kEpiWarpBytes;
-    float* stage = reinterpret_cast<float*>(epi_base);
-    int* m_pix = reinterpret_cast<int*>(epi_base + 32 * kStagePitch * 4);        // [32] output pixel, -1 = skip
-    int* m_ho = m_pix + 32;
-    int* m_wo = m_ho + 32;
-    int* m_utt = m_wo + 32;
-    float* m_raw = reinterpret_cast<float*>(m_utt + 32);
-    const int sub = lane >> 3;                // row within a group of 4
-    const int c4 = (lane & 7) * 4;            // 4 channels per lane
+    uint8_t* epi_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + ew * kEpiWarpBytes;
+    uint4* stage = reinterpret_cast<uint4*>(epi_base);                 // [32 rows][4 x 16 B], XOR swizzled
+    int4* meta = reinterpret_cast<int4*>(epi_base + 32 * 64);          // [32] {pixel, tf row, utt, raw bits}
+    const int sub = lane >> 2;                // row within a group of 8
+    const int jc = lane & 3;                  // 16-byte column slot: channels 4 jc .. 4 jc + 3 of the chunk
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    struct LoadSet {
+      float4 b[4], t[4];
+      uint2 x[4];
+    };
     uint32_t it = 0;
+    long long w_full = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int n0 = (tile % n_tiles) * p.BN;
-      if (p.debug_skip_epilogue) {
+      if (p.debug_skip_epilogue == 1) {
         ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
         ptx::tc_fence_before();
         ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
         continue;
       }
-      bool waited = false;
-      for (int i = 0; i < MT; ++i) {
-        const int m0 = (tile / n_tiles) * (MT * 128) + i * 128;
-        if (m0 >= p.M) break;
-        {
-          // per-row metadata, computed by the thread that owns the row in TMEM
-          const int m = m0 + q * 32 + lane;
-          bool valid = m < p.M;
-          int unit = 0, ho = 0, wo = 0;
-          if (valid) {
-            unit = m / hw;
-            const int rem = m - unit * hw;
-            ho = rem / p.Wq;
-            wo = rem - ho * p.Wq;
-            valid = (ho < p.Ho) && (wo < p.Wo);
-          }
-          int pix = -1, utt = 0;
-          float rawv = 0.f;
-          if (valid) {
-            utt = p.units.utt ? p.units.utt[unit] : 0;
-            if (e.r1_vec) {
-              const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
-              if (frame >= p.units.lo[unit] && frame < p.units.hi[unit]) rawv = e.raw[(size_t)frame * 201 + wo * e.r1_sw];
-            }
-            if (e.head) {
-              pix = unit;
-              utt = p.units.frame[unit];     // head: the centre frame row replaces the utterance index
-            } else if (e.o_mode == 1) {
-              pix = (unit * e.o_W + wo) * e.o_H + ho;
-            } else {
-              const int y = ho + e.o_oy, x = wo + e.o_ox;
-              const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
-              pix = (int)(plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw));
-            }
-          }
-          m_pix[lane] = pix; m_ho[lane] = ho; m_wo[lane] = wo; m_utt[lane] = utt; m_raw[lane] = rawv;
-        }
-        __syncwarp();
-        int pixs[8];
-        float4 fb[8], ft[8], ff[8];
-        uint2 fx[8];
-        // Issues every global load of one 32-column chunk (read-only path) ahead of the accumulator wait /
-        // TMEM read so that the memory latency overlaps them.
-        auto issue_loads = [&](int c0) {
-          const int col = n0 + c0 + c4;
-          const bool lane_ok = c4 < p.BN - c0 && !e.head;
+      const int tile_m0 = (tile / n_tiles) * (MT * 128);
+      // ---- per-row metadata of every sub-tile, computed by the thread that owns the row (loads overlap) ----
+      int4 md[4];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int r = g * 4 + sub;
-            pixs[g] = m_pix[r];
+      for (int i = 0; i < 4; ++i) {
+        md[i] = make_int4(-1, 0, 0, 0);
+        if (i >= MT) continue;
+        const int m = tile_m0 + i * 128 + q * 32 + lane;
+        if (m >= p.M) continue;
+        const int unit = m / hw;
+        const int rem = m - unit * hw;
+        const int ho = rem / p.Wq;
+        const int wo = rem - ho * p.Wq;
+        if (ho >= p.Ho || wo >= p.Wo) continue;
+        int pix, utt = p.units.utt[unit];
+        float rawv = 0.f;
+        if (e.r1_vec) {
+          const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
+          if (frame >= p.units.lo[unit] && frame < p.units.hi[unit]) rawv = __ldg(e.raw + (size_t)frame * 201 + wo * e.r1_sw);
+        }
+        if (e.head) {
+          pix = unit;
+          utt = p.units.frame[unit];         // head: the centre frame row replaces the utterance index
+        } else if (e.o_mode == 1) {
+          pix = (unit * e.o_W + wo) * e.o_H + ho;
+        } else {
+          const int y = ho + e.o_oy, x = wo + e.o_ox;
+          const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
+          pix = (int)(plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw));
+        }
+        md[i] = make_int4(pix, ho * p.Wo + wo, utt, __float_as_int(rawv));
+      }
+      bool waited = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i >= MT) break;
+        const int m0 = tile_m0 + i * 128;
+        if (m0 >= p.M) break;
+        __syncwarp();
+        meta[lane] = md[i];
+        __syncwarp();
+        int pixs[4], tfr[4], utts[4];
+        float raws[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int4 mm = meta[g * 8 + sub];
+          pixs[g] = mm.x; tfr[g] = mm.y; utts[g] = mm.z; raws[g] = __int_as_float(mm.w);
+        }
+        // every global load of one 16-column chunk (read-only path)
+        auto issue_loads = [&](LoadSet& L, int c0) {
+          const int col = n0 + c0 + 4 * jc;
+          const bool lane_ok = c0 < p.BN && !e.head && p.debug_skip_epilogue != 2;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
             const bool ok = lane_ok && pixs[g] >= 0;
-            fb[g] = ok ? __ldg(reinterpret_cast<const float4*>(e.bias + (size_t)m_utt[r] * e.bias_stride + col)) : zero4;
-            ft[g] = (ok && e.ttab) ? __ldg(reinterpret_cast<const float4*>(e.ttab + (size_t)m_ho[r] * p.N + col)) : zero4;
-            ff[g] = (ok && e.ftab) ? __ldg(reinterpret_cast<const float4*>(e.ftab + (size_t)m_wo[r] * p.N + col)) : zero4;
-            fx[g] = (ok && e.res) ? __ldg(reinterpret_cast<const uint2*>(e.res + (size_t)(m0 + q * 32 + r) * e.res_C + col)) : make_uint2(0u, 0u);
+            L.b[g] = ok ? __ldg(reinterpret_cast<const float4*>(e.bias + (size_t)utts[g] * e.bias_stride + col)) : zero4;
+            L.t[g] = (ok && e.tftab) ? __ldg(reinterpret_cast<const float4*>(e.tftab + (size_t)tfr[g] * p.N + col)) : zero4;
+            L.x[g] = (ok && e.res) ? __ldg(reinterpret_cast<const uint2*>(e.res + (size_t)(m0 + q * 32 + g * 8 + sub) * e.res_C + col)) : make_uint2(0u, 0u);
           }
         };
-        issue_loads(0);
-        if (!waited) {
-          ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
-          ptx::tc_fence_after();
-          waited = true;
-        }
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + i * p.BN;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-          const int width = min(32, p.BN - c0);
-          // phase 1: TMEM (thread = row) -> staging
-          if (width == 32) {
-            uint32_t v[32];
-            ptx::tmem_ld32(t_addr + c0, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(stage + lane * kStagePitch + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
+        // one 16-column chunk: TMEM -> swizzled staging -> 4 lanes per row
+        auto process = [&](const LoadSet& L, int c0) {
+          {
             uint32_t v[16];
             ptx::tmem_ld16(t_addr + c0, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(stage + lane * kStagePitch + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              stage[lane * 4 + ((j ^ (lane >> 1)) & 3)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           __syncwarp();
-          // phase 2: 8 lanes per row, 4 channels per lane
-          if (c4 < width) {
-            const int col = n0 + c0 + c4;
-            if (e.head) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          const int col = n0 + c0 + 4 * jc;
+          if (e.head) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const int r = g * 4 + sub;
-                const int pix = m_pix[r];
-                if (pix < 0) continue;
-                const float4 f = *reinterpret_cast<const float4*>(stage + r * kStagePitch + c4);
-                const float* raw_row = e.raw + (size_t)m_utt[r] * 201;
-                float* o = e.out_f32 + (size_t)pix * 201;
-                if (col < 201) o[col] = f.x + b.x + raw_row[col];
-                if (col + 1 < 201) o[col + 1] = f.y + b.y + raw_row[col + 1];
-                if (col + 2 < 201) o[col + 2] = f.z + b.z + raw_row[col + 2];
-                if (col + 3 < 201) o[col + 3] = f.w + b.w + raw_row[col + 3];
-              }
-            } else {
-              const float4 rs = e.res ? __ldg(reinterpret_cast<const float4*>(e.res_scale + col)) : zero4;
-              const float4 r1 = e.r1_vec ? __ldg(reinterpret_cast<const float4*>(e.r1_vec + col)) : zero4;
+            for (int g = 0; g < 4; ++g) {
+              if (pixs[g] < 0) continue;
+              const int r = g * 8 + sub;
+              const uint4 u = stage[r * 4 + ((jc ^ (r >> 1)) & 3)];
+              const float* raw_row = e.raw + (size_t)utts[g] * 201;
+              float* o = e.out_f32 + (size_t)pixs[g] * 201;
+              if (col < 201) o[col] = __uint_as_float(u.x) + b.x + raw_row[col];
+              if (col + 1 < 201) o[col + 1] = __uint_as_float(u.y) + b.y + raw_row[col + 1];
+              if (col + 2 < 201) o[col + 2] = __uint_as_float(u.z) + b.z + raw_row[col + 2];
+              if (col + 3 < 201) o[col + 3] = __uint_as_float(u.w) + b.w + raw_row[col + 3];
+            }
+          } else {
+            const float4 rs = e.res ? __ldg(reinterpret_cast<const float4*>(e.res_scale + col)) : zero4;
+            const float4 r1 = e.r1_vec ? __ldg(reinterpret_cast<const float4*>(e.r1_vec + col)) : zero4;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (pixs[g] < 0) continue;
-                const int r = g * 4 + sub;
-                float4 f = *reinterpret_cast<const float4*>(stage + r * kStagePitch + c4);
-                f.x += fb[g].x + ft[g].x + ff[g].x; f.y += fb[g].y + ft[g].y + ff[g].y;
-                f.z += fb[g].z + ft[g].z + ff[g].z; f.w += fb[g].w + ft[g].w + ff[g].w;
-                const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&fx[g].x));
-                const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&fx[g].y));
-                f.x = fmaf(rs.x, x0.x, f.x); f.y = fmaf(rs.y, x0.y, f.y);
-                f.z = fmaf(rs.z, x1.x, f.z); f.w = fmaf(rs.w, x1.y, f.w);
-                if (e.r1_vec) {
-                  const float rawv = m_raw[r];
-                  f.x = fmaf(r1.x, rawv, f.x); f.y = fmaf(r1.y, rawv, f.y);
-                  f.z = fmaf(r1.z, rawv, f.z); f.w = fmaf(r1.w, rawv, f.w);
-                }
-                if (e.relu) {
-                  f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
-                }
-                uint2 o;
-                o.x = pack_half2(f.x, f.y);
-                o.y = pack_half2(f.z, f.w);
-                *reinterpret_cast<uint2*>(e.out + (size_t)pixs[g] * e.out_C + col) = o;
+            for (int g = 0; g < 4; ++g) {
+              if (pixs[g] < 0) continue;
+              const int r = g * 8 + sub;
+              const uint4 u = stage[r * 4 + ((jc ^ (r >> 1)) & 3)];
+              float4 f = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+              f.x += L.b[g].x + L.t[g].x; f.y += L.b[g].y + L.t[g].y;
+              f.z += L.b[g].z + L.t[g].z; f.w += L.b[g].w + L.t[g].w;
+              const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&L.x[g].x));
+              const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&L.x[g].y));
+              f.x = fmaf(rs.x, x0.x, f.x); f.y = fmaf(rs.y, x0.y, f.y);
+              f.z = fmaf(rs.z, x1.x, f.z); f.w = fmaf(rs.w, x1.y, f.w);
+              f.x = fmaf(r1.x, raws[g], f.x); f.y = fmaf(r1.y, raws[g], f.y);
+              f.z = fmaf(r1.z, raws[g], f.z); f.w = fmaf(r1.w, raws[g], f.w);
+              if (e.relu) {
+                f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
               }
+              uint2 o;
+              o.x = pack_half2(f.x, f.y);
+              o.y = pack_half2(f.z, f.w);
+              if (p.debug_skip_epilogue != 3) *reinterpret_cast<uint2*>(e.out + (size_t)pixs[g] * e.out_C + col) = o;
             }
           }
           __syncwarp();                       // staging is overwritten by the next chunk
-          if (c0 + 32 < p.BN) issue_loads(c0 + 32);
+        };
+        // chunks of this warp: c = (half + i) & 1, +2, ... (the two warps of a quarter alternate)
+        LoadSet A, B;
+        int c0 = ((half + i) & 1) * 16;
+        issue_loads(A, c0);
+        if (!waited) {
+          ptx::mbar_wait_timed(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4, &w_full);
+          ptx::tc_fence_after();
+          waited = true;
         }
-        __syncwarp();                         // metadata is overwritten by the next sub-tile
+        for (; c0 < p.BN; c0 += 64) {
+          issue_loads(B, c0 + 32);            // in flight while chunk c0 is processed (no-op past the end)
+          process(A, c0);
+          if (c0 + 32 < p.BN) {
+            issue_loads(A, c0 + 64);
+            process(B, c0 + 32);
+          }
+        }
       }
       if (!waited) ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
     }
+    if (p.debug_stats && threadIdx.x == 96) atomicAdd(p.debug_stats + 3, (unsigned long long)w_full);
   }
 
   ptx::tc_fence_before();
@@ -424,7 +437,7 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
   if (desc_mode >> 1) { cfg.il = desc_mode >> 1; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
-  if (cfg.nb < 4) return cudaErrorInvalidValue;
+  if (cfg.nb < 4) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight
   const int tiles = ((p.M + cfg.mt * 128 - 1) / (cfg.mt * 128)) * (p.N / p.BN);
   const int grid = tiles < n_sm ? tiles : n_sm;
   gemm_shift_kernel<<<grid, kGemmThreads, smem, s>>>(mapA0, mapA1, mapB, p, cfg);

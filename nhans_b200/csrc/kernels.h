@@ -21,8 +21,7 @@ struct UnitTable {
 struct EpiDev {
   const float* bias;        // [n_utt or 1][bias_stride] (+ column offset already applied)
   int bias_stride;          // 0: one shared row
-  const float* ttab;        // [Ho][N] or null
-  const float* ftab;        // [Wo][N] or null
+  const float* tftab;       // [Ho * Wo][N] time + frequency embedding, or null
   const __half* res;        // identity residual rows [m][res_C] or null
   int res_C;
   const float* res_scale;   // [N]
@@ -65,6 +64,7 @@ struct GemmDev {
   EpiDev epi;
   int* err_flag;
   int debug_skip_epilogue;  // measurement aid: epilogue warps only release the accumulator
+  unsigned long long* debug_stats;   // optional [8] cycle counters (wait times per role), or null
 };
 
 struct DirectDev {
@@ -77,7 +77,7 @@ struct DirectDev {
   EpiDev epi;
 };
 
-constexpr int kGemmThreads = 224;     // A producer, B producer, MMA issuer, 4 epilogue warps
+constexpr int kGemmThreads = 352;     // A producer, B producer, MMA issuer, 8 epilogue warps
 int gemm_smem_bytes(int BN, int num_kb, GemmCfg* cfg);
 cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,

@@ -58,8 +58,7 @@ direct_conv64_kernel(const DirectDev p) {
   }
   const int utt = p.units_tab.utt ? p.units_tab.utt[unit] : 0;
   const float4* b4 = reinterpret_cast<const float4*>(e.bias + (size_t)utt * e.bias_stride);
-  const float4* t4 = e.ttab ? reinterpret_cast<const float4*>(e.ttab + (size_t)ho * 64) : nullptr;
-  const float4* f4 = e.ftab ? reinterpret_cast<const float4*>(e.ftab + (size_t)wo * 64) : nullptr;
+  const float4* t4 = e.tftab ? reinterpret_cast<const float4*>(e.tftab + ((size_t)ho * p.Wo + wo) * 64) : nullptr;
   const int y = ho + e.o_oy, x = wo + e.o_ox;
   const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
   const long long pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw);
@@ -72,7 +71,6 @@ direct_conv64_kernel(const DirectDev p) {
       const int n4 = 2 * g + h;
       float4 b = b4[n4];
       if (t4) { const float4 t = t4[n4]; b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w; }
-      if (f4) { const float4 t = f4[n4]; b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w; }
       v[4 * h] = acc[4 * n4] + b.x;
       v[4 * h + 1] = acc[4 * n4 + 1] + b.y;
       v[4 * h + 2] = acc[4 * n4 + 2] + b.z;

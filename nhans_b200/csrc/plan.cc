@@ -226,12 +226,12 @@ struct Builder {
       cond_consts.push_back({off, constant});
       std::vector<double> T = cont_embed(w, site_scope + "_temb", Ho, C);
       std::vector<double> F = cont_embed(w, site_scope + "_femb", Wo, C);
-      e->ttab.resize(T.size());
-      e->ftab.resize(F.size());
+      // one combined table (there is no L1 left for small tables on the GPU, so one L2 read beats two)
+      e->tftab.resize((size_t)Ho * Wo * C);
       for (int i = 0; i < Ho; ++i)
-        for (int c = 0; c < C; ++c) e->ttab[(size_t)i * C + c] = (float)(T[(size_t)i * C + c] * s[c]);
-      for (int i = 0; i < Wo; ++i)
-        for (int c = 0; c < C; ++c) e->ftab[(size_t)i * C + c] = (float)(F[(size_t)i * C + c] * s[c]);
+        for (int j = 0; j < Wo; ++j)
+          for (int c = 0; c < C; ++c)
+            e->tftab[((size_t)i * Wo + j) * C + c] = (float)((T[(size_t)i * C + c] + F[(size_t)j * C + c]) * s[c]);
     } else {
       e->bias.resize(C);
       for (int c = 0; c < C; ++c) e->bias[c] = (float)constant[c];

@@ -75,12 +75,11 @@ struct KGroup {
 };
 
 struct Epilogue {
-  // v = acc + bias[utt * bias_stride + n] + ttab[ho][n] + ftab[wo][n]
+  // v = acc + bias[utt * bias_stride + n] + tftab[ho * Wo + wo][n]
   //       + res_scale[n] * res[m][n] + r1_vec[n] * raw(n, ho, wo);  v = relu ? max(v, 0) : v
   int cond_off = -1;              // >= 0: per-utterance bias = column block of the conditioning table
   std::vector<float> bias;        // constant bias [N] (cond_off < 0)
-  std::vector<float> ttab;        // [Ho][N] or empty
-  std::vector<float> ftab;        // [Wo][N] or empty
+  std::vector<float> tftab;       // [Ho * Wo][N]: time + frequency embedding (scaled), or empty
   int res_buf = -1;               // identity residual: buffer with the same row indexing
   std::vector<float> res_scale;   // [N]
   std::vector<float> r1_vec;      // rank-1 term on the raw spectrogram (1x1 transform with Cin = 1)

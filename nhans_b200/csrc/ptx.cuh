@@ -78,6 +78,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   }
 }
 
+// mbar_wait that adds the cycles spent waiting to *acc (debug statistics)
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, int* err_flag, int tag, long long* acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err_flag, tag);
+  *acc += clock64() - t0;
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

@@ -57,7 +57,7 @@ struct EpiCtx {
 };
 
 // Shared epilogue (gemm_tc.cu epilogue warps / direct_conv64_kernel tail).
-void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int unit, int ho, int wo, long long m,
+void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int Wo, int unit, int ho, int wo, long long m,
               const float* acc, std::vector<std::vector<float>>& bufs) {
   const int utt = c.units->utt[unit];
   const float* bias = E.cond_off >= 0 ? c.cond + (size_t)utt * c.net->plan.cond.n_cols + E.cond_off : E.bias.data();
@@ -68,8 +68,7 @@ void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int un
   }
   for (int n = 0; n < N; ++n) {
     float v = acc[n] + bias[n];
-    if (!E.ttab.empty()) v += E.ttab[(size_t)ho * N + n];
-    if (!E.ftab.empty()) v += E.ftab[(size_t)wo * N + n];
+    if (!E.tftab.empty()) v += E.tftab[((size_t)ho * Wo + wo) * N + n];
     if (E.res_buf >= 0) v = fmaf(E.res_scale[n], bufs[E.res_buf][(size_t)m * c.net->plan.bufs[E.res_buf].C + n], v);
     if (!E.r1_vec.empty()) v = fmaf(E.r1_vec[n], rawv, v);
     if (E.relu) v = v > 0.f ? v : 0.f;
@@ -104,7 +103,7 @@ void run_net(Net& net, int units_n, const Units& units, const float* raw, const 
           for (int n = 0; n < D.N; ++n) acc[n] = fmaf(x, w[n], acc[n]);
         }
       }
-      epilogue(c, D.epi, D.out, D.N, unit, ho, wo, 0, acc, net.bufs);
+      epilogue(c, D.epi, D.out, D.N, D.Wo, unit, ho, wo, 0, acc, net.bufs);
     }
   }
   for (size_t li = 0; li < P.gemm.size(); ++li) {
@@ -135,7 +134,7 @@ void run_net(Net& net, int units_n, const Units& units, const float* raw, const 
           }
         }
       }
-      epilogue(c, L.epi, L.out, L.N, unit, ho, wo, m, acc.data(), net.bufs);
+      epilogue(c, L.epi, L.out, L.N, L.Wo, unit, ho, wo, m, acc.data(), net.bufs);
     }
   }
 }

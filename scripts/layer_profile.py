@@ -37,3 +37,11 @@ st = eng.profile_get(0)
 print("all GEMM layers: %.1f ms, %.1f TFLOP/s;  direct conv %.1f ms" % (st["ms"] / 2, st["flops"] / st["ms"] / 1e9, eng.profile_get(3)["ms"] / 2))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(layers, open(os.path.join(ROOT, "gpurun_out", "layers_skip%s.json" % os.environ.get("NHANS_DEBUG_SKIP_EPILOGUE", "0")), "w"))
+if os.environ.get("NHANS_DEBUG_STATS"):
+    import ctypes
+    print("wait cycles per layer (sum over 148 CTAs, %): tmem_empty | a_full | b_full | epi waits tmem_full | of MMA-warp total")
+    for i, l in enumerate(layers):
+        st = (ctypes.c_uint64 * 8)()
+        eng.lib.nhans_debug_layer_stats(eng.h, 0, i, st)
+        tot = max(1, st[4])
+        print("%-22s %5.1f%% %5.1f%% %5.1f%%   epi %5.1f%%   total %.2e" % (l["name"], 100 * st[0] / tot, 100 * st[1] / tot, 100 * st[2] / tot, 100 * st[3] / tot, tot))
