@@ -17,15 +17,19 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // frame units.frame[n] + r + raw_oh of the fp32 log-magnitude array; rows outside the clip and outside
 // [0, Hin) read 0.0, which is the zero padding of pad_1D_for_windowing (SN/apply.py:170-173) and of the
 // 'SAME' convolution at once - the [T, 35, 201] window tensor is never materialised.
+constexpr int kDirectPitch = 68;                       // floats per staged pixel row (64 + 4: conflict-free float4 access)
 __global__ void __launch_bounds__(128)
 direct_conv64_kernel(const DirectDev p) {
-  extern __shared__ float s_w[];                       // [kh*kw][64]
+  extern __shared__ float s_w[];                       // [kh*kw][64] | 4 x [32][kDirectPitch] staging | metadata
   const int taps = p.kh * p.kw;
+  float* s_stage = s_w + taps * 64;
+  int* s_meta = reinterpret_cast<int*>(s_stage + 4 * 32 * kDirectPitch);
   for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) s_w[i] = p.w[i];
   __syncthreads();
   const long long total = (long long)p.units * p.Ho * p.Wo;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = idx < total;
+  if (!valid) idx = total - 1;                          // tail threads compute a duplicate and store nothing
   const int unit = (int)(idx / (p.Ho * p.Wo));
   const int rem = (int)(idx - (long long)unit * p.Ho * p.Wo);
   const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
@@ -56,26 +60,41 @@ direct_conv64_kernel(const DirectDev p) {
       }
     }
   }
+  // Epilogue through a warp-private shared-memory transpose: 8 lanes then cover one pixel's 64 channels, so
+  // the table loads and the fp16 stores of a warp touch whole 128-byte lines instead of 32 scattered ones.
   const int utt = p.units_tab.utt ? p.units_tab.utt[unit] : 0;
-  const float4* b4 = reinterpret_cast<const float4*>(e.bias + (size_t)utt * e.bias_stride);
-  const float4* t4 = e.tftab ? reinterpret_cast<const float4*>(e.tftab + ((size_t)ho * p.Wo + wo) * 64) : nullptr;
-  const int y = ho + e.o_oy, x = wo + e.o_ox;
-  const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
-  const long long pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw);
-  uint4* out = reinterpret_cast<uint4*>(e.out + pix * e.out_C);
+  const int yy = ho + e.o_oy, xx = wo + e.o_ox;
+  const int plane = (yy % e.o_sh) * e.o_sw + (xx % e.o_sw);
+  const long long pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(yy / e.o_sh) * e.o_Wq + (xx / e.o_sw);
+  const int lane = threadIdx.x & 31;
+  float* st = s_stage + (threadIdx.x >> 5) * (32 * kDirectPitch);
+  long long* s_pix = reinterpret_cast<long long*>(s_meta) + (threadIdx.x >> 5) * 32;
+  int* s_tf = s_meta + 2 * 4 * 32 + (threadIdx.x >> 5) * 64;
+  __syncwarp();
 #pragma unroll
+  for (int n = 0; n < 16; ++n)
+    *reinterpret_cast<float4*>(st + lane * kDirectPitch + 4 * n) = make_float4(acc[4 * n], acc[4 * n + 1], acc[4 * n + 2], acc[4 * n + 3]);
+  s_pix[lane] = valid ? pix : -1;
+  s_tf[2 * lane] = valid ? (ho * p.Wo + wo) : 0;
+  s_tf[2 * lane + 1] = utt;
+  __syncwarp();
+  const int sub = lane >> 3, cg = (lane & 7) * 8;
+#pragma unroll 2
   for (int g = 0; g < 8; ++g) {
-    float v[8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int n4 = 2 * g + h;
-      float4 b = b4[n4];
-      if (t4) { const float4 t = t4[n4]; b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w; }
-      v[4 * h] = acc[4 * n4] + b.x;
-      v[4 * h + 1] = acc[4 * n4 + 1] + b.y;
-      v[4 * h + 2] = acc[4 * n4 + 2] + b.z;
-      v[4 * h + 3] = acc[4 * n4 + 3] + b.w;
+    const int r = g * 4 + sub;
+    const long long opix = s_pix[r];
+    if (opix < 0) continue;
+    const float4 a0 = *reinterpret_cast<const float4*>(st + r * kDirectPitch + cg);
+    const float4 a1 = *reinterpret_cast<const float4*>(st + r * kDirectPitch + cg + 4);
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + (size_t)s_tf[2 * r + 1] * e.bias_stride + cg);
+    float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    if (e.tftab) {
+      const float4* t4 = reinterpret_cast<const float4*>(e.tftab + (size_t)s_tf[2 * r] * 64 + cg);
+      const float4 t0 = __ldg(t4), t1 = __ldg(t4 + 1);
+      b0.x += t0.x; b0.y += t0.y; b0.z += t0.z; b0.w += t0.w;
+      b1.x += t1.x; b1.y += t1.y; b1.z += t1.z; b1.w += t1.w;
     }
+    float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
     if (e.relu) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -83,7 +102,7 @@ direct_conv64_kernel(const DirectDev p) {
     uint4 o;
     o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
     o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
-    out[g] = o;
+    *reinterpret_cast<uint4*>(e.out + opix * e.out_C + cg) = o;
   }
 }
 
@@ -169,7 +188,8 @@ cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p) {
   const long long total = (long long)p.units * p.Ho * p.Wo;
   const int threads = 128;
   const long long blocks = (total + threads - 1) / threads;
-  direct_conv64_kernel<<<(unsigned)blocks, threads, p.kh * p.kw * 64 * sizeof(float), s>>>(p);
+  const size_t smem = (size_t)p.kh * p.kw * 64 * 4 + 4 * 32 * kDirectPitch * 4 + 2 * 4 * 32 * 4 + 4 * 64 * 4;
+  direct_conv64_kernel<<<(unsigned)blocks, threads, smem, s>>>(p);
   return cudaGetLastError();
 }
 
