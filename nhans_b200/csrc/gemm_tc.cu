@@ -325,8 +325,20 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         auto process = [&](const LoadSet& L, int c0) {
           {
             uint32_t v[16];
-            ptx::tmem_ld16(t_addr + c0, v);
-            ptx::tmem_ld_wait();
+            if (p.debug_skip_epilogue != 5) {
+              ptx::tmem_ld16(t_addr + c0, v);
+              ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = lane + j;
+            }
+            if (p.debug_skip_epilogue == 4) {
+              uint32_t x = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x ^= v[j];
+              if (x == 0x12345678u) stage[lane] = make_uint4(x, x, x, x);   // keeps the load alive
+              return;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               stage[lane * 4 + ((j ^ (lane >> 1)) & 3)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
