@@ -50,6 +50,7 @@ struct GemmLayerDev {
   __half* w = nullptr;
   KGroupDev* groups = nullptr;
   float *bias = nullptr, *tftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
+  uint16_t *ttab16 = nullptr, *ftab16 = nullptr;
   CUtensorMap mapA0, mapA1, mapB;
 };
 
@@ -204,6 +205,8 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
     if ((rc = upload(ctx, net, groups, &D.groups))) return rc;
     if ((rc = upload(ctx, net, L.epi.bias, &D.bias))) return rc;
     if ((rc = upload(ctx, net, L.epi.tftab, &D.tftab))) return rc;
+    if ((rc = upload(ctx, net, L.epi.ttab16, &D.ttab16))) return rc;
+    if ((rc = upload(ctx, net, L.epi.ftab16, &D.ftab16))) return rc;
     if ((rc = upload(ctx, net, L.epi.res_scale, &D.res_scale))) return rc;
     if ((rc = upload(ctx, net, L.epi.r1_vec, &D.r1_vec))) return rc;
     for (int a = 0; a < 2; ++a) {
@@ -307,6 +310,7 @@ EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const flo
   e.r1_vec = r1_vec; e.r1_sh = E.r1_sh; e.r1_sw = E.r1_sw; e.raw_oh = E.raw_oh;
   e.raw = raw;
   e.relu = E.relu; e.head = E.head;
+  e.pair = E.pair; e.n_real = E.n_real; e.pair_W = E.pair_W; e.res_off0 = E.res_off[0]; e.res_off1 = E.res_off[1];
   fill_out(e, net, out);
   e.out_f32 = out_f32;
   return e;
@@ -340,6 +344,10 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.Hq = L.Hq; g.Wq = L.Wq; g.Ho = L.Ho; g.Wo = L.Wo;
     g.units = ut;
     g.epi = make_epi(net, L.epi, L.out, D.bias, D.tftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);
+    g.epi.ttab16 = reinterpret_cast<const __half*>(D.ttab16);
+    g.epi.ftab16 = reinterpret_cast<const __half*>(D.ftab16);
+    g.epi.tab_H = L.Ho;
+    g.epi.tab_W = L.epi.pair ? L.epi.pair_W : L.Wo;
     g.err_flag = ctx->err_flag_dev;
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
     g.debug_stats = ctx->debug_stats ? ctx->debug_stats + 8 * ((&net == &ctx->tower ? 64 : 0) + (int)i) : nullptr;

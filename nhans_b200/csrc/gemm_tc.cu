@@ -39,6 +39,11 @@ constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
 constexpr int kMaxGroups = 212;
 constexpr int kMaxA = 8, kMaxB = 16;
 constexpr int kSmemLimit = 227 * 1024;
+#ifdef NHANS_ISSUERS_FIRST
+constexpr int kWarpA = 0, kWarpB = 1, kWarpMma = 2, kEpiWarp0 = 3;
+#else
+constexpr int kWarpA = 8, kWarpB = 9, kWarpMma = 10, kEpiWarp0 = 0;
+#endif
 
 struct __align__(8) Ctrl {
   uint64_t a_full[kMaxA], a_empty[kMaxA];
@@ -130,6 +135,218 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   }
 }
 
+// Epilogue flavours (compile-time: the epilogue is instruction bound, every runtime flag costs issue slots)
+constexpr int kEpiPair = 1;       // pixel-pair rows (plan.h Epilogue::pair)
+constexpr int kEpiRes = 2;        // + res_scale[c] * x (identity residual)
+constexpr int kEpiR1 = 4;         // + r1_vec[c] * raw spectrogram value (1x1 transform with Cin = 1)
+constexpr int kEpiTabS = 8;       // time / frequency embedding tables (fp16) resident in shared memory
+constexpr int kEpiTabG = 16;      // combined fp32 embedding table read from global memory
+constexpr int kEpiHead = 32;      // last_dense: fp32 out + centre frame
+
+// One epilogue warp.  ew = 0..7: TMEM lane quarter q = ew & 3, and the two warps of a quarter (half = ew >> 2)
+// take alternate 16-column chunks.  Per chunk: tcgen05.ld (thread = row) -> XOR-swizzled 32 x 16 fp32 transpose
+// in shared memory -> 4 lanes per row x 4 channels, so that global loads / stores are coalesced.  The loads
+// of chunk k + 1 are in flight while chunk k is processed; slot metadata is computed one slot ahead.
+template <int EPI>
+__device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, const GemmCfg& cfg, int ew, int lane,
+                                              uint32_t tmem_base, int num_tiles, int n_tiles, const __half* s_ttab,
+                                              const __half* s_ftab) {
+  constexpr bool kPair = EPI & kEpiPair, kRes = EPI & kEpiRes, kR1 = EPI & kEpiR1, kTabS = EPI & kEpiTabS,
+                 kTabG = EPI & kEpiTabG, kHead = EPI & kEpiHead;
+  const EpiDev& e = p.epi;
+  const int MT = cfg.mt;
+  const int q = ew & 3, half = ew >> 2;
+  const int hw = p.Hq * p.Wq;
+  uint8_t* epi_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + ew * kEpiWarpBytes;
+  uint4* stage = reinterpret_cast<uint4*>(epi_base);                 // [32 rows][4 x 16 B], XOR swizzled
+  int4* meta = reinterpret_cast<int4*>(epi_base + 32 * 64);          // [32] {pixel, (ho << 16) | wo, utt, raw bits}
+  const int sub = lane >> 2;                // row within a group of 8
+  const int jc = lane & 3;                  // 16-byte column slot: channels 4 jc .. 4 jc + 3 of the chunk
+  const int NV = kPair ? 2 * MT : MT;       // slots per tile: sub-tile i, or (sub-tile i, pixel j) for pair rows
+  const int vcols = kPair ? e.n_real : p.BN;
+  const int tab_C = kPair ? e.n_real : p.N; // row pitch of the embedding tables
+  const int tab_W = kPair ? e.pair_W : p.Wo;
+  struct LoadSet {
+    float4 b[4], t[4];
+    uint2 x[4];
+  };
+  uint32_t it = 0;
+  long long w_full = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+    const int n0 = (tile % n_tiles) * p.BN;
+    if (p.debug_skip_epilogue == 1) {
+      ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+      continue;
+    }
+    const int tile_m0 = (tile / n_tiles) * (MT * 128);
+    // metadata of the row this thread owns in slot v (its TMEM lane)
+    auto slot_meta = [&](int v) -> int4 {
+      if (v >= NV) return make_int4(-1, 0, 0, 0);
+      const int i = kPair ? (v >> 1) : v, j = kPair ? (v & 1) : 0;
+      const int m = tile_m0 + i * 128 + q * 32 + lane;
+      if (m >= p.M) return make_int4(-1, 0, 0, 0);
+      const int unit = m / hw;
+      const int rem = m - unit * hw;
+      const int ho = rem / p.Wq;
+      int wo = rem - ho * p.Wq;
+      if (ho >= p.Ho || wo >= p.Wo) return make_int4(-1, 0, 0, 0);
+      if (kPair) {
+        wo = 2 * wo + j;
+        if (wo >= e.pair_W) return make_int4(-1, 0, 0, 0);
+      }
+      int pix, utt = p.units.utt[unit];
+      float rawv = 0.f;
+      if (kR1) {
+        const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
+        if (frame >= p.units.lo[unit] && frame < p.units.hi[unit]) rawv = __ldg(e.raw + (size_t)frame * 201 + wo * e.r1_sw);
+      }
+      if (kHead) {
+        pix = unit;
+        utt = p.units.frame[unit];           // head: the centre frame row replaces the utterance index
+      } else if (e.o_mode == 1) {
+        pix = (unit * e.o_W + wo) * e.o_H + ho;
+      } else {
+        const int y = ho + e.o_oy, x = wo + e.o_ox;
+        const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
+        pix = (int)(plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw));
+      }
+      return make_int4(pix, (ho << 16) | wo, utt, __float_as_int(rawv));
+    };
+    bool waited = false;
+    int4 md_next = slot_meta(0);
+#pragma unroll 1
+    for (int v = 0; v < NV; ++v) {
+      const int i = kPair ? (v >> 1) : v;
+      const int m0 = tile_m0 + i * 128;
+      if (m0 >= p.M) break;
+      const int4 md_cur = md_next;
+      md_next = slot_meta(v + 1);             // its loads are in flight while slot v is processed
+      __syncwarp();
+      meta[lane] = md_cur;
+      __syncwarp();
+      // per row group g (row 8 g + sub of the warp's 32 rows): element offsets hoisted out of the chunk loop
+      bool ok[4];
+      float raws[4];
+      size_t o_out[4], o_res[4], o_bias[4], o_tf[4];
+      int o_t[4], o_f[4];
+      const int col0 = n0 + 4 * jc;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int4 mm = meta[g * 8 + sub];
+        ok[g] = mm.x >= 0;
+        raws[g] = __int_as_float(mm.w);
+        const int ho = mm.y >> 16, wo = mm.y & 0xffff;
+        o_out[g] = (size_t)mm.x * (kHead ? 201 : e.out_C) + col0;
+        o_bias[g] = (size_t)mm.z * (kHead ? 201 : e.bias_stride) + col0;   // head: mm.z = centre frame row of raw
+        if (kRes) {
+          const long long rr = (long long)m0 + q * 32 + g * 8 + sub + (kPair ? ((v & 1) ? e.res_off1 : e.res_off0) : 0);
+          o_res[g] = (size_t)rr * e.res_C + col0;
+        }
+        if (kTabS) { o_t[g] = ho * tab_C + col0; o_f[g] = wo * tab_C + col0; }
+        if (kTabG) o_tf[g] = (size_t)(ho * tab_W + wo) * tab_C + col0;
+      }
+      auto issue_loads = [&](LoadSet& L, int c0) {
+        if (kHead || c0 >= vcols || p.debug_skip_epilogue == 2) return;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (!ok[g]) continue;
+          L.b[g] = __ldg(reinterpret_cast<const float4*>(e.bias + o_bias[g] + c0));
+          if (kTabG) L.t[g] = __ldg(reinterpret_cast<const float4*>(e.tftab + o_tf[g] + c0));
+          if (kRes) L.x[g] = __ldg(reinterpret_cast<const uint2*>(e.res + o_res[g] + c0));
+        }
+      };
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + i * p.BN + (kPair ? (v & 1) * e.n_real : 0);
+      auto process = [&](const LoadSet& L, int c0) {
+        {
+          uint32_t tv[16];
+          ptx::tmem_ld16(t_addr + c0, tv);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            stage[lane * 4 + ((j ^ (lane >> 1)) & 3)] = make_uint4(tv[4 * j], tv[4 * j + 1], tv[4 * j + 2], tv[4 * j + 3]);
+        }
+        __syncwarp();
+        float4 rs, r1;
+        if (kRes) rs = __ldg(reinterpret_cast<const float4*>(e.res_scale + col0 + c0));
+        if (kR1) r1 = __ldg(reinterpret_cast<const float4*>(e.r1_vec + col0 + c0));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (!ok[g]) continue;
+          const int r = g * 8 + sub;
+          const uint4 u = stage[r * 4 + ((jc ^ (r >> 1)) & 3)];
+          float4 f = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+          if (kHead) {
+            const int col = col0 + c0;
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+            const float* raw_row = e.raw + o_bias[g] - col0;
+            float* o = e.out_f32 + o_out[g] - col0;
+            if (col < 201) o[col] = f.x + b.x + raw_row[col];
+            if (col + 1 < 201) o[col + 1] = f.y + b.y + raw_row[col + 1];
+            if (col + 2 < 201) o[col + 2] = f.z + b.z + raw_row[col + 2];
+            if (col + 3 < 201) o[col + 3] = f.w + b.w + raw_row[col + 3];
+            continue;
+          }
+          if (p.debug_skip_epilogue != 2) { f.x += L.b[g].x; f.y += L.b[g].y; f.z += L.b[g].z; f.w += L.b[g].w; }
+          if (kTabG && p.debug_skip_epilogue != 2) { f.x += L.t[g].x; f.y += L.t[g].y; f.z += L.t[g].z; f.w += L.t[g].w; }
+          if (kTabS) {
+            // fp16 tables: add time + frequency rows as half2, then widen once
+            const uint2 tv = *reinterpret_cast<const uint2*>(s_ttab + o_t[g] + c0);
+            const uint2 fv = *reinterpret_cast<const uint2*>(s_ftab + o_f[g] + c0);
+            const float2 s0 = __half22float2(__hadd2(*reinterpret_cast<const __half2*>(&tv.x), *reinterpret_cast<const __half2*>(&fv.x)));
+            const float2 s1 = __half22float2(__hadd2(*reinterpret_cast<const __half2*>(&tv.y), *reinterpret_cast<const __half2*>(&fv.y)));
+            f.x += s0.x; f.y += s0.y; f.z += s1.x; f.w += s1.y;
+          }
+          if (kRes && p.debug_skip_epilogue != 2) {
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&L.x[g].x));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&L.x[g].y));
+            f.x = fmaf(rs.x, x0.x, f.x); f.y = fmaf(rs.y, x0.y, f.y);
+            f.z = fmaf(rs.z, x1.x, f.z); f.w = fmaf(rs.w, x1.y, f.w);
+          }
+          if (kR1) {
+            f.x = fmaf(r1.x, raws[g], f.x); f.y = fmaf(r1.y, raws[g], f.y);
+            f.z = fmaf(r1.z, raws[g], f.z); f.w = fmaf(r1.w, raws[g], f.w);
+          }
+          if (e.relu) {
+            f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+          }
+          uint2 o;
+          o.x = pack_half2(f.x, f.y);
+          o.y = pack_half2(f.z, f.w);
+          if (p.debug_skip_epilogue != 3) *reinterpret_cast<uint2*>(e.out + o_out[g] + c0) = o;
+        }
+        __syncwarp();                         // staging is overwritten by the next chunk
+      };
+      // chunks of this warp: the two warps of a quarter alternate 16-column chunks
+      LoadSet A, B;
+      int c0 = ((half + v) & 1) * 16;
+      issue_loads(A, c0);
+      if (!waited) {
+        ptx::mbar_wait_timed(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4, &w_full);
+        ptx::tc_fence_after();
+        waited = true;
+      }
+#pragma unroll 1
+      for (; c0 < vcols; c0 += 64) {
+        issue_loads(B, c0 + 32);              // in flight while chunk c0 is processed (no-op past the end)
+        process(A, c0);
+        if (c0 + 32 < vcols) {
+          issue_loads(A, c0 + 64);
+          process(B, c0 + 32);
+        }
+      }
+    }
+    if (!waited) ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+  }
+  if (p.debug_stats && ew == 0 && lane == 0) atomicAdd(p.debug_stats + 3, (unsigned long long)w_full);
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const GemmDev p, const GemmCfg cfg) {
@@ -150,6 +367,15 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int num_groups = p.num_groups;
 
   for (int i = threadIdx.x; i < num_groups; i += blockDim.x) ctrl->groups[i] = p.groups[i];
+  // optional shared-memory copies of the fp16 time / frequency embedding tables (after the epilogue staging)
+  __half* s_ttab = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + kEpiBytes);
+  const int tab_C = p.epi.pair ? p.epi.n_real : p.N;
+  __half* s_ftab = s_ttab + p.epi.tab_H * tab_C;
+  if (cfg.tab_bytes) {
+    const int nt = p.epi.tab_H * tab_C / 8, nf = p.epi.tab_W * tab_C / 8;       // 16-byte units
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) reinterpret_cast<uint4*>(s_ttab)[i] = reinterpret_cast<const uint4*>(p.epi.ttab16)[i];
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) reinterpret_cast<uint4*>(s_ftab)[i] = reinterpret_cast<const uint4*>(p.epi.ftab16)[i];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < cfg.na; ++s) { ptx::mbar_init(&ctrl->a_full[s], 1); ptx::mbar_init(&ctrl->a_empty[s], 1); }
     for (int s = 0; s < cfg.nb; ++s) { ptx::mbar_init(&ctrl->b_full[s], 1); ptx::mbar_init(&ctrl->b_empty[s], 1); }
@@ -160,12 +386,12 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kWarpA && lane == 0) {
     ptx::tma_prefetch_desc(&mapA0);
     ptx::tma_prefetch_desc(&mapA1);
     ptx::tma_prefetch_desc(&mapB);
   }
-  if (warp == 10) ptx::tmem_alloc(&ctrl->tmem_base, 512);
+  if (warp == kWarpMma) ptx::tmem_alloc(&ctrl->tmem_base, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -173,7 +399,7 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   // Warp roles: the hardware arbiter favours the highest warp id of a sub-partition, so the single-lane
   // issuers (warps 8-10) out-prioritise the ALU-heavy epilogue warps (0-7) they share a scheduler with.
-  if (warp == 8) {
+  if (warp == kWarpA) {
     // ===================== A producer: one slab per (group, sub-tile) =====================
     // (whole warp runs the loop; one elected lane issues the TMA - keeps the control flow warp-uniform)
     uint32_t slot = 0, phase = 0;
@@ -193,7 +419,7 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWarpB) {
     // ===================== B producer =====================
     if (cfg.resident) {
       // the whole packed weight matrix fits: load every k-block once, never release
@@ -223,198 +449,19 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
     if (cfg.il == 4) mma_issuer<4>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
     else if (cfg.il == 2) mma_issuer<2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
     else mma_issuer<1>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
   } else {
     // ===================== epilogue (warps 0..7) =====================
-    // With ~225 KB of shared memory in use there is no L1 left: every table / residual read is an L2 round
-    // trip of a few thousand cycles under load, so the epilogue is latency bound.  Hence: two warps per TMEM
-    // lane quarter (alternating 16-column chunks), small chunks whose loads fit in registers twice, and the
-    // loads of chunk k+1 in flight while chunk k is transposed and stored.
-    const EpiDev& e = p.epi;
-    const int ew = warp;
-    const int q = warp & 3;                   // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                 // which of the two warps of the quarter
-    const int hw = p.Hq * p.Wq;
-    uint8_t* epi_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + ew * kEpiWarpBytes;
-    uint4* stage = reinterpret_cast<uint4*>(epi_base);                 // [32 rows][4 x 16 B], XOR swizzled
-    int4* meta = reinterpret_cast<int4*>(epi_base + 32 * 64);          // [32] {pixel, tf row, utt, raw bits}
-    const int sub = lane >> 2;                // row within a group of 8
-    const int jc = lane & 3;                  // 16-byte column slot: channels 4 jc .. 4 jc + 3 of the chunk
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    struct LoadSet {
-      float4 b[4], t[4];
-      uint2 x[4];
-    };
-    uint32_t it = 0;
-    long long w_full = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int n0 = (tile % n_tiles) * p.BN;
-      if (p.debug_skip_epilogue == 1) {
-        ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
-        continue;
-      }
-      const int tile_m0 = (tile / n_tiles) * (MT * 128);
-      // ---- per-row metadata of every sub-tile, computed by the thread that owns the row (loads overlap) ----
-      int4 md[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        md[i] = make_int4(-1, 0, 0, 0);
-        if (i >= MT) continue;
-        const int m = tile_m0 + i * 128 + q * 32 + lane;
-        if (m >= p.M) continue;
-        const int unit = m / hw;
-        const int rem = m - unit * hw;
-        const int ho = rem / p.Wq;
-        const int wo = rem - ho * p.Wq;
-        if (ho >= p.Ho || wo >= p.Wo) continue;
-        int pix, utt = p.units.utt[unit];
-        float rawv = 0.f;
-        if (e.r1_vec) {
-          const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
-          if (frame >= p.units.lo[unit] && frame < p.units.hi[unit]) rawv = __ldg(e.raw + (size_t)frame * 201 + wo * e.r1_sw);
-        }
-        if (e.head) {
-          pix = unit;
-          utt = p.units.frame[unit];         // head: the centre frame row replaces the utterance index
-        } else if (e.o_mode == 1) {
-          pix = (unit * e.o_W + wo) * e.o_H + ho;
-        } else {
-          const int y = ho + e.o_oy, x = wo + e.o_ox;
-          const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
-          pix = (int)(plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw));
-        }
-        md[i] = make_int4(pix, ho * p.Wo + wo, utt, __float_as_int(rawv));
-      }
-      bool waited = false;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i >= MT) break;
-        const int m0 = tile_m0 + i * 128;
-        if (m0 >= p.M) break;
-        __syncwarp();
-        meta[lane] = md[i];
-        __syncwarp();
-        int pixs[4], tfr[4], utts[4];
-        float raws[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int4 mm = meta[g * 8 + sub];
-          pixs[g] = mm.x; tfr[g] = mm.y; utts[g] = mm.z; raws[g] = __int_as_float(mm.w);
-        }
-        // every global load of one 16-column chunk (read-only path)
-        auto issue_loads = [&](LoadSet& L, int c0) {
-          const int col = n0 + c0 + 4 * jc;
-          const bool lane_ok = c0 < p.BN && !e.head && p.debug_skip_epilogue != 2;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const bool ok = lane_ok && pixs[g] >= 0;
-            L.b[g] = ok ? __ldg(reinterpret_cast<const float4*>(e.bias + (size_t)utts[g] * e.bias_stride + col)) : zero4;
-            L.t[g] = (ok && e.tftab) ? __ldg(reinterpret_cast<const float4*>(e.tftab + (size_t)tfr[g] * p.N + col)) : zero4;
-            L.x[g] = (ok && e.res) ? __ldg(reinterpret_cast<const uint2*>(e.res + (size_t)(m0 + q * 32 + g * 8 + sub) * e.res_C + col)) : make_uint2(0u, 0u);
-          }
-        };
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + i * p.BN;
-        // one 16-column chunk: TMEM -> swizzled staging -> 4 lanes per row
-        auto process = [&](const LoadSet& L, int c0) {
-          {
-            uint32_t v[16];
-            if (p.debug_skip_epilogue != 5) {
-              ptx::tmem_ld16(t_addr + c0, v);
-              ptx::tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = lane + j;
-            }
-            if (p.debug_skip_epilogue == 4) {
-              uint32_t x = 0;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) x ^= v[j];
-              if (x == 0x12345678u) stage[lane] = make_uint4(x, x, x, x);   // keeps the load alive
-              return;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              stage[lane * 4 + ((j ^ (lane >> 1)) & 3)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          __syncwarp();
-          const int col = n0 + c0 + 4 * jc;
-          if (e.head) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (pixs[g] < 0) continue;
-              const int r = g * 8 + sub;
-              const uint4 u = stage[r * 4 + ((jc ^ (r >> 1)) & 3)];
-              const float* raw_row = e.raw + (size_t)utts[g] * 201;
-              float* o = e.out_f32 + (size_t)pixs[g] * 201;
-              if (col < 201) o[col] = __uint_as_float(u.x) + b.x + raw_row[col];
-              if (col + 1 < 201) o[col + 1] = __uint_as_float(u.y) + b.y + raw_row[col + 1];
-              if (col + 2 < 201) o[col + 2] = __uint_as_float(u.z) + b.z + raw_row[col + 2];
-              if (col + 3 < 201) o[col + 3] = __uint_as_float(u.w) + b.w + raw_row[col + 3];
-            }
-          } else {
-            const float4 rs = e.res ? __ldg(reinterpret_cast<const float4*>(e.res_scale + col)) : zero4;
-            const float4 r1 = e.r1_vec ? __ldg(reinterpret_cast<const float4*>(e.r1_vec + col)) : zero4;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (pixs[g] < 0) continue;
-              const int r = g * 8 + sub;
-              const uint4 u = stage[r * 4 + ((jc ^ (r >> 1)) & 3)];
-              float4 f = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-              f.x += L.b[g].x + L.t[g].x; f.y += L.b[g].y + L.t[g].y;
-              f.z += L.b[g].z + L.t[g].z; f.w += L.b[g].w + L.t[g].w;
-              const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&L.x[g].x));
-              const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&L.x[g].y));
-              f.x = fmaf(rs.x, x0.x, f.x); f.y = fmaf(rs.y, x0.y, f.y);
-              f.z = fmaf(rs.z, x1.x, f.z); f.w = fmaf(rs.w, x1.y, f.w);
-              f.x = fmaf(r1.x, raws[g], f.x); f.y = fmaf(r1.y, raws[g], f.y);
-              f.z = fmaf(r1.z, raws[g], f.z); f.w = fmaf(r1.w, raws[g], f.w);
-              if (e.relu) {
-                f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
-              }
-              uint2 o;
-              o.x = pack_half2(f.x, f.y);
-              o.y = pack_half2(f.z, f.w);
-              if (p.debug_skip_epilogue != 3) *reinterpret_cast<uint2*>(e.out + (size_t)pixs[g] * e.out_C + col) = o;
-            }
-          }
-          __syncwarp();                       // staging is overwritten by the next chunk
-        };
-        // chunks of this warp: c = (half + i) & 1, +2, ... (the two warps of a quarter alternate)
-        LoadSet A, B;
-        int c0 = ((half + i) & 1) * 16;
-        issue_loads(A, c0);
-        if (!waited) {
-          ptx::mbar_wait_timed(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4, &w_full);
-          ptx::tc_fence_after();
-          waited = true;
-        }
-        for (; c0 < p.BN; c0 += 64) {
-          issue_loads(B, c0 + 32);            // in flight while chunk c0 is processed (no-op past the end)
-          process(A, c0);
-          if (c0 + 32 < p.BN) {
-            issue_loads(A, c0 + 64);
-            process(B, c0 + 32);
-          }
-        }
-      }
-      if (!waited) ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
-    }
-    if (p.debug_stats && threadIdx.x == 0) atomicAdd(p.debug_stats + 3, (unsigned long long)w_full);
+    epilogue_warp<EPI>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 10) {
+  if (warp == kWarpMma) {
     __syncwarp();
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -423,39 +470,78 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
 }  // namespace
 
-int gemm_smem_bytes(int BN, int num_kb, GemmCfg* cfg) {
+int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, GemmCfg* cfg) {
   const int b_bytes = BN * 128;
   GemmCfg c;
+  // shared-memory tables only where the epilogue is the critical path (short main loops: BN <= 128)
+  c.tab_bytes = (BN <= 128 && tab_bytes > 0) ? ((tab_bytes + 127) & ~127) : 0;
   c.mt = 256 / BN < 1 ? 1 : 256 / BN;
   c.na = 4;
-  const int budget = kSmemLimit - 1024 - kCtrlBytes - kEpiBytes - c.na * kSlabBytes;
+  const int budget = kSmemLimit - 1024 - kCtrlBytes - kEpiBytes - c.tab_bytes - c.na * kSlabBytes;
   c.nb = budget / b_bytes;
   if (c.nb > kMaxB) c.nb = kMaxB;
   c.resident = (num_kb <= c.nb) ? 1 : 0;
   c.desc_mode = 0;
   c.il = c.mt >= 2 ? 2 : 1;
   if (cfg) *cfg = c;
-  return 1024 + c.na * kSlabBytes + c.nb * b_bytes + kCtrlBytes + kEpiBytes;
+  return 1024 + c.na * kSlabBytes + c.nb * b_bytes + kCtrlBytes + kEpiBytes + c.tab_bytes;
 }
 
-cudaError_t gemm_configure() {
-  return cudaFuncSetAttribute(gemm_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+namespace {
+template <int EPI>
+cudaError_t launch_flavour(cudaStream_t s, int grid, int smem, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                           const GemmDev& p, const GemmCfg& cfg) {
+  static bool configured = false;           // per process; every device of one box runs the same binary
+  cudaError_t e = cudaFuncSetAttribute(gemm_shift_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  if (e != cudaSuccess) return e;
+  configured = true;
+  (void)configured;
+  gemm_shift_kernel<EPI><<<grid, kGemmThreads, smem, s>>>(a0, a1, b, p, cfg);
+  return cudaGetLastError();
 }
+}  // namespace
+
+cudaError_t gemm_configure() { return cudaSuccess; }
 
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
                         const CUtensorMap& mapB, const GemmDev& p, int desc_mode) {
   if (p.M <= 0) return cudaSuccess;
   if (p.num_groups > kMaxGroups || p.BN % 16 != 0 || p.BN > 256 || p.N % p.BN != 0) return cudaErrorInvalidValue;
   GemmCfg cfg;
-  const int smem = gemm_smem_bytes(p.BN, p.num_kb, &cfg);
+  const int tab_bytes = (p.epi.ttab16 && p.epi.ftab16) ? (p.epi.tab_H + p.epi.tab_W) * (p.epi.pair ? p.epi.n_real : p.N) * 2 : 0;
+  const int smem = gemm_smem_bytes(p.BN, p.num_kb, tab_bytes, &cfg);
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
   if (desc_mode >> 1) { cfg.il = desc_mode >> 1; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
   if (cfg.nb < 4) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight
   const int tiles = ((p.M + cfg.mt * 128 - 1) / (cfg.mt * 128)) * (p.N / p.BN);
   const int grid = tiles < n_sm ? tiles : n_sm;
-  gemm_shift_kernel<<<grid, kGemmThreads, smem, s>>>(mapA0, mapA1, mapB, p, cfg);
-  return cudaGetLastError();
+  const EpiDev& e = p.epi;
+  int fl = 0;
+  if (e.head) fl = kEpiHead;
+  else {
+    if (e.pair) fl |= kEpiPair;
+    if (e.res) fl |= kEpiRes;
+    if (e.r1_vec) fl |= kEpiR1;
+    if (e.tftab) fl |= cfg.tab_bytes ? kEpiTabS : kEpiTabG;
+  }
+#define NHANS_FLAVOUR(F) case F: return launch_flavour<F>(s, grid, smem, mapA0, mapA1, mapB, p, cfg);
+  switch (fl) {
+    NHANS_FLAVOUR(0)                                   // tower conv1 / conv2 with GEMM transform, last_conv
+    NHANS_FLAVOUR(kEpiR1)                              // tower block-1 conv2
+    NHANS_FLAVOUR(kEpiHead)                            // last_dense
+    NHANS_FLAVOUR(kEpiTabS)                            // conditioned conv1 / conv2+GEMM transform, BN <= 128
+    NHANS_FLAVOUR(kEpiTabS | kEpiRes)
+    NHANS_FLAVOUR(kEpiTabS | kEpiR1)
+    NHANS_FLAVOUR(kEpiTabG)                            // the same with BN = 256 (tables stay in global memory)
+    NHANS_FLAVOUR(kEpiTabG | kEpiRes)
+    NHANS_FLAVOUR(kEpiTabG | kEpiR1)
+    NHANS_FLAVOUR(kEpiPair | kEpiTabS)                 // pixel-pair rows (64-channel stage)
+    NHANS_FLAVOUR(kEpiPair | kEpiTabS | kEpiRes)
+    NHANS_FLAVOUR(kEpiPair | kEpiTabS | kEpiR1)
+    default: return cudaErrorInvalidValue;
+  }
+#undef NHANS_FLAVOUR
 }
 
 }  // namespace nhans

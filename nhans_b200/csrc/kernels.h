@@ -22,6 +22,9 @@ struct EpiDev {
   const float* bias;        // [n_utt or 1][bias_stride] (+ column offset already applied)
   int bias_stride;          // 0: one shared row
   const float* tftab;       // [Ho * Wo][N] time + frequency embedding, or null
+  const __half* ttab16;     // fp16 [tab_H][C] / [tab_W][C] copies for the shared-memory-resident variant, or null
+  const __half* ftab16;
+  int tab_H, tab_W;
   const __half* res;        // identity residual rows [m][res_C] or null
   int res_C;
   const float* res_scale;   // [N]
@@ -30,6 +33,8 @@ struct EpiDev {
   const float* raw;         // fp32 spectrogram rows [frame][201]
   int relu;
   int head;                 // 1: out_f32[n][201] = acc + bias + raw[frame(n)]
+  int pair, n_real, pair_W; // pixel-pair rows: column = j * n_real + c (plan.h Epilogue)
+  long long res_off0, res_off1;
   // output grid (plan.h Grid)
   __half* out;
   int out_C;
@@ -51,6 +56,7 @@ struct GemmCfg {              // chosen by the host per layer shape
   int resident;               // all k-blocks of B fit in the ring: load once
   int desc_mode;              // 1: set the descriptor base-offset field for row-shifted slabs
   int il;                     // sub-tiles whose MMAs are interleaved (1, 2 or 4; divides mt, <= na)
+  int tab_bytes;              // > 0: the fp16 time / frequency tables are staged in shared memory
 };
 
 struct GemmDev {
@@ -78,7 +84,7 @@ struct DirectDev {
 };
 
 constexpr int kGemmThreads = 352;     // A producer, B producer, MMA issuer, 8 epilogue warps
-int gemm_smem_bytes(int BN, int num_kb, GemmCfg* cfg);
+int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, GemmCfg* cfg);
 cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
                         const CUtensorMap& mapB, const GemmDev& p, int desc_mode);

@@ -80,11 +80,20 @@ struct Epilogue {
   int cond_off = -1;              // >= 0: per-utterance bias = column block of the conditioning table
   std::vector<float> bias;        // constant bias [N] (cond_off < 0)
   std::vector<float> tftab;       // [Ho * Wo][N]: time + frequency embedding (scaled), or empty
+  std::vector<uint16_t> ttab16;   // the same embeddings kept separate in fp16, [Ho][C] and [Wo][C]: small enough
+  std::vector<uint16_t> ftab16;   //   (~30 KB) to live in shared memory for the layers whose epilogue is the bottleneck
   int res_buf = -1;               // identity residual: buffer with the same row indexing
   std::vector<float> res_scale;   // [N]
   std::vector<float> r1_vec;      // rank-1 term on the raw spectrogram (1x1 transform with Cin = 1)
   int r1_sh = 1, r1_sw = 1;       // raw frame = win_frame[n] + ho * r1_sh + raw_oh, bin = wo * r1_sw
   int raw_oh = 0;
+  // Pixel-pair mode (64-channel stride-1 blocks): a GEMM row is the pixel pair (h, 2 w'), (h, 2 w' + 1) and
+  // column n = j * n_real + c is channel c of pixel j, so that the MMA runs with N = 128 (an M = 128 MMA with
+  // N = 64 costs as much as N = 128).  Tables / res_scale / r1_vec are indexed by c.
+  int pair = 0;
+  int n_real = 0;                 // channels per pixel (pair mode), else N
+  int pair_W = 0;                 // logical width: pixel j of a pair is valid when 2 w' + j < pair_W
+  int64_t res_off[2] = {0, 0};    // residual row of pixel j relative to the GEMM row
   int relu = 1;
   int head = 0;                   // 1: fp32 output [n][201] = acc + bias + raw[center frame] (main.py:238-242)
 };

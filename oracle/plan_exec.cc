@@ -57,7 +57,7 @@ struct EpiCtx {
 };
 
 // Shared epilogue (gemm_tc.cu epilogue warps / direct_conv64_kernel tail).
-void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int Wo, int unit, int ho, int wo, long long m,
+void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int Wo, int unit, int ho, int wo, long long res_row,
               const float* acc, std::vector<std::vector<float>>& bufs) {
   const int utt = c.units->utt[unit];
   const float* bias = E.cond_off >= 0 ? c.cond + (size_t)utt * c.net->plan.cond.n_cols + E.cond_off : E.bias.data();
@@ -69,7 +69,7 @@ void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int Wo
   for (int n = 0; n < N; ++n) {
     float v = acc[n] + bias[n];
     if (!E.tftab.empty()) v += E.tftab[((size_t)ho * Wo + wo) * N + n];
-    if (E.res_buf >= 0) v = fmaf(E.res_scale[n], bufs[E.res_buf][(size_t)m * c.net->plan.bufs[E.res_buf].C + n], v);
+    if (E.res_buf >= 0) v = fmaf(E.res_scale[n], bufs[E.res_buf][(size_t)res_row * c.net->plan.bufs[E.res_buf].C + n], v);
     if (!E.r1_vec.empty()) v = fmaf(E.r1_vec[n], rawv, v);
     if (E.relu) v = v > 0.f ? v : 0.f;
     if (E.head) {
@@ -134,7 +134,15 @@ void run_net(Net& net, int units_n, const Units& units, const float* raw, const 
           }
         }
       }
-      epilogue(c, L.epi, L.out, L.N, L.Wo, unit, ho, wo, m, acc.data(), net.bufs);
+      if (L.epi.pair) {
+        // pixel-pair rows: columns [j * C, (j + 1) * C) are pixel (ho, 2 wo + j)
+        const int C = L.epi.n_real;
+        for (int j = 0; j < 2; ++j)
+          if (2 * wo + j < L.epi.pair_W)
+            epilogue(c, L.epi, L.out, C, L.epi.pair_W, unit, ho, 2 * wo + j, m + L.epi.res_off[j], acc.data() + j * C, net.bufs);
+      } else {
+        epilogue(c, L.epi, L.out, L.N, L.Wo, unit, ho, wo, m, acc.data(), net.bufs);
+      }
     }
   }
 }
