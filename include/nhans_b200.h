@@ -96,6 +96,13 @@ int nhans_upload(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, in
 int nhans_run(nhans_ctx* ctx);
 int nhans_download(nhans_ctx* ctx, int16_t* out_i16, float* out_f32, float* mixproc_f32);
 
+/* Post-mix outputs of apply_snc for the batch nhans_run just processed (SN/apply.py:456-472), computed on the GPU
+ * in one fused pass: mixed_processed = iSTFT(input spectrum), removed = mixed_processed - denoised,
+ * snr_est[u] = mean(denoised^2) / mean(removed^2), compensated = denoised + removed * (ac ? snr_est / 20 : compensate).
+ * Any output may be NULL; copies are enqueued on the context stream (nhans_sync). */
+int nhans_postmix(nhans_ctx* ctx, float compensate, int ac, float* mixed_f32, float* removed_f32, float* compensated_f32,
+                  float* snr_est);
+
 /* Pinned host memory for the copies above. */
 int nhans_host_alloc(int64_t bytes, void** out);
 void nhans_host_free(void* p);

@@ -13,7 +13,7 @@ SO_PATH = os.path.join(_HERE, "libnhans_b200.so")
 SYMBOLS = [
     "nhans_create", "nhans_destroy", "nhans_last_error", "nhans_load_weights", "nhans_normalise", "nhans_stft",
     "nhans_embed", "nhans_masknet", "nhans_istft", "nhans_output_offsets", "nhans_enhance_batch", "nhans_sync",
-    "nhans_upload", "nhans_run", "nhans_download", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
+    "nhans_upload", "nhans_run", "nhans_download", "nhans_postmix", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
     "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset",
     "nhans_profile_get_layer", "nhans_plan_json",
     "nhans_debug_read_buffer", "nhans_debug_layer_stats", "nhans_device_info",
@@ -59,6 +59,7 @@ def load():
     lib.nhans_upload.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.nhans_run.argtypes = [vp]
     lib.nhans_download.argtypes = [vp, vp, vp, vp]
+    lib.nhans_postmix.argtypes = [vp, c.c_float, i32, vp, vp, vp, vp]
     lib.nhans_sync.argtypes = [vp]
     lib.nhans_host_alloc.argtypes = [i64, c.POINTER(vp)]
     lib.nhans_host_free.argtypes = [vp]

@@ -81,7 +81,7 @@ struct Batch {
   int max_frames = 0;
   DBuf mix, a, b, d_mix_offs, d_a_offs, d_b_offs, d_frame_offs, d_out_offs, d_ctx_frame_offs;
   DBuf peak_mix, peak_a, peak_b;
-  DBuf logmag, phase, den, ctxlm_a, ctxlm_b, emb_a, emb_b, cond, out_i16, out_f32, mixproc;
+  DBuf logmag, phase, den, ctxlm_a, ctxlm_b, emb_a, emb_b, cond, out_i16, out_f32, mixproc, removed, comp, sums, snr;
 };
 
 }  // namespace
@@ -487,7 +487,8 @@ void nhans_destroy(nhans_ctx* ctx) {
   Batch& b = ctx->batch;
   for (DBuf* d : {&b.mix, &b.a, &b.b, &b.d_mix_offs, &b.d_a_offs, &b.d_b_offs, &b.d_frame_offs, &b.d_out_offs,
                   &b.d_ctx_frame_offs, &b.peak_mix, &b.peak_a, &b.peak_b, &b.logmag, &b.phase, &b.den, &b.ctxlm_a,
-                  &b.ctxlm_b, &b.emb_a, &b.emb_b, &b.cond, &b.out_i16, &b.out_f32, &b.mixproc, &ctx->silent_emb})
+                  &b.ctxlm_b, &b.emb_a, &b.emb_b, &b.cond, &b.out_i16, &b.out_f32, &b.mixproc, &b.removed, &b.comp, &b.sums,
+                  &b.snr, &ctx->silent_emb})
     d->release();
   for (auto& t : ctx->tmp) t.release();
   for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
@@ -828,6 +829,34 @@ int nhans_download(nhans_ctx* ctx, int16_t* out_i16, float* out_f32, float* mixp
   }
   if (out_i16) CK(cudaMemcpyAsync(out_i16, b.out_i16.p, b.total_out * 2, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_f32) CK(cudaMemcpyAsync(out_f32, b.out_f32.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return NHANS_OK;
+}
+
+int nhans_postmix(nhans_ctx* ctx, float compensate, int ac, float* mixed_f32, float* removed_f32, float* compensated_f32,
+                  float* snr_est) {
+  if (!ctx) return NHANS_ERR_ARG;
+  Batch& b = ctx->batch;
+  if (!b.done) return fail(ctx, NHANS_ERR_STATE, "nhans_run has not produced a batch");
+  CK(cudaSetDevice(ctx->device));
+  CK(b.removed.ensure(b.total_out * 4 + 4));
+  CK(b.comp.ensure(b.total_out * 4 + 4));
+  CK(b.sums.ensure(sizeof(double) * 2 * b.U));
+  CK(b.snr.ensure(sizeof(float) * b.U));
+  {
+    ProfScope ps(ctx, 2, 0, 3.0 * b.total_frames * kBins * 4 + 12.0 * b.total_out);
+    CK(launch_istft_post(ctx->stream, b.den.as<float>(), b.logmag.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
+                         b.d_out_offs.as<long long>(), b.U, b.max_frames, nullptr, b.mixproc.as<float>(), b.removed.as<float>(),
+                         b.sums.as<double>()));
+  }
+  {
+    ProfScope ps(ctx, 4, 0, 0);
+    CK(launch_compensate(ctx->stream, b.out_f32.as<float>(), b.removed.as<float>(), b.d_out_offs.as<long long>(), b.U,
+                         b.sums.as<double>(), compensate, ac, compensated_f32 ? b.comp.as<float>() : nullptr, b.snr.as<float>()));
+  }
+  if (mixed_f32) CK(cudaMemcpyAsync(mixed_f32, b.mixproc.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (removed_f32) CK(cudaMemcpyAsync(removed_f32, b.removed.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (compensated_f32) CK(cudaMemcpyAsync(compensated_f32, b.comp.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (snr_est) CK(cudaMemcpyAsync(snr_est, b.snr.p, sizeof(float) * b.U, cudaMemcpyDeviceToHost, ctx->stream));
   return NHANS_OK;
 }
 

@@ -115,67 +115,89 @@ __global__ void normalise_kernel(const int16_t* __restrict__ pcm, const long lon
     out[out_offs[u] + i] = (float)((double)pcm[offs[u] + i] / denom);
 }
 
-// grid: (ceil((max_frames + 2) / kOH), U).  Output hop h (160 samples) sums frames h-2, h-1, h.
-__global__ void __launch_bounds__(kThreads)
-istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, const long long* __restrict__ frame_offs,
-             const long long* __restrict__ out_offs, const int* __restrict__ peak, float* __restrict__ out_f32,
-             int16_t* __restrict__ out_i16) {
+// Shared-memory working set of one inverse-STFT block (kOH output hops from kOH + 2 frames).
+struct IstftSmem {
+  float2 s[(kOH + 2) * kBinsD];           // spectrum, then FFT scratch, then the time-domain frames
+  float2 a[(kOH + 2) * 200];
+  float2 tw200[200];
+  float2 tw400[201];
+  float winv[kWin];
+};
+
+__device__ __forceinline__ void istft_load_tables(IstftSmem& sm) {
+  for (int i = threadIdx.x; i < 200; i += blockDim.x) sm.tw200[i] = g_tw200[i];
+  for (int i = threadIdx.x; i < 201; i += blockDim.x) sm.tw400[i] = g_tw400[i];
+  for (int i = threadIdx.x; i < kWin; i += blockDim.x) sm.winv[i] = g_winv[i];
+}
+
+// exp(logmag) e^{j phase} -> irfft-400 -> synthesis window for frames fa .. fa + kOH + 1 of clip rows
+// [row0, row0 + T); leaves the windowed frames in sm.s viewed as float [kOH + 2][400].
+__device__ __forceinline__ float* istft_frames(IstftSmem& sm, const float* __restrict__ logmag,
+                                               const float* __restrict__ phase, long long row0, int T, int fa) {
   constexpr int NF = kOH + 2;
-  __shared__ float2 s_s[NF * kBinsD];     // spectrum, then FFT scratch, then the time-domain frames
-  __shared__ float2 s_a[NF * 200];
-  __shared__ float2 s_tw200[200];
-  __shared__ float2 s_tw400[201];
-  __shared__ float s_winv[kWin];
-  const int u = blockIdx.y;
-  const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
-  if (T <= 0) return;
-  const int h0 = blockIdx.x * kOH;        // first output hop
-  if (h0 >= T + 2) return;
-  const int fa = h0 - 2;                  // first frame needed (may be negative)
-  for (int i = threadIdx.x; i < 200; i += blockDim.x) s_tw200[i] = g_tw200[i];
-  for (int i = threadIdx.x; i < 201; i += blockDim.x) s_tw400[i] = g_tw400[i];
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) s_winv[i] = g_winv[i];
-  const long long row0 = frame_offs[u];
+  __syncthreads();                         // previous use of the buffers is over
   for (int i = threadIdx.x; i < NF * kBinsD; i += blockDim.x) {
     const int f = i / kBinsD, k = i - f * kBinsD;
     const int t = fa + f;
-    float2 s = make_float2(0.f, 0.f);
+    float2 v = make_float2(0.f, 0.f);
     if (t >= 0 && t < T) {
       const size_t o = (size_t)(row0 + t) * kBinsD + k;
       const float a = expf(logmag[o]);
       float sn, cs;
       sincosf(phase[o], &sn, &cs);
-      s = make_float2(a * cs, a * sn);
-      if (k == 0 || k == 200) s.y = 0.f;  // irfft ignores the imaginary part of DC / Nyquist
+      v = make_float2(a * cs, a * sn);
+      if (k == 0 || k == 200) v.y = 0.f;  // irfft ignores the imaginary part of DC / Nyquist
     }
-    s_s[i] = s;
+    sm.s[i] = v;
   }
   __syncthreads();
   // Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]),  k = 0..199
   for (int i = threadIdx.x; i < NF * 200; i += blockDim.x) {
     const int f = i / 200, k = i - f * 200;
-    s_a[i] = irfft_pre(s_s + f * kBinsD, k, s_tw400);
+    sm.a[i] = irfft_pre(sm.s + f * kBinsD, k, sm.tw400);
   }
   __syncthreads();
-  fft200_block<true>(s_a, s_s, s_a, NF, s_tw200);
+  fft200_block<true>(sm.a, sm.s, sm.a, NF, sm.tw200);
   // frames: y_f[2m] = Re z[m] / 400, y_f[2m+1] = Im z[m] / 400, times the synthesis window
-  float* s_y = reinterpret_cast<float*>(s_s);          // [NF][400]
+  float* s_y = reinterpret_cast<float*>(sm.s);          // [NF][400]
   for (int i = threadIdx.x; i < NF * 200; i += blockDim.x) {
     const int f = i / 200, m = i - f * 200;
-    const float2 z = s_a[i];
-    s_y[f * kWin + 2 * m] = z.x * (1.0f / 400.0f) * s_winv[2 * m];
-    s_y[f * kWin + 2 * m + 1] = z.y * (1.0f / 400.0f) * s_winv[2 * m + 1];
+    const float2 z = sm.a[i];
+    s_y[f * kWin + 2 * m] = z.x * (1.0f / 400.0f) * sm.winv[2 * m];
+    s_y[f * kWin + 2 * m + 1] = z.y * (1.0f / 400.0f) * sm.winv[2 * m + 1];
   }
   __syncthreads();
+  return s_y;
+}
+
+// 3-frame gather overlap-add of sample i of the block (local hop hl = i / 160)
+__device__ __forceinline__ float ola_sample(const float* s_y, int i) {
+  const int hl = i / kHop, r = i - hl * kHop;
+  // frame local index f = hl + 2 - j covers sample offset r + 160 j, j = 0..2 (zero frames outside [0, T))
+  float acc = s_y[(hl + 2) * kWin + r] + s_y[(hl + 1) * kWin + r + kHop];
+  if (r + 2 * kHop < kWin) acc += s_y[hl * kWin + r + 2 * kHop];
+  return acc;
+}
+
+// grid: (ceil((max_frames + 2) / kOH), U).  Output hop h (160 samples) sums frames h-2, h-1, h.
+__global__ void __launch_bounds__(kThreads)
+istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, const long long* __restrict__ frame_offs,
+             const long long* __restrict__ out_offs, const int* __restrict__ peak, float* __restrict__ out_f32,
+             int16_t* __restrict__ out_i16) {
+  __shared__ IstftSmem sm;
+  const int u = blockIdx.y;
+  const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
+  if (T <= 0) return;
+  const int h0 = blockIdx.x * kOH;        // first output hop
+  if (h0 >= T + 2) return;
+  istft_load_tables(sm);
+  const float* s_y = istft_frames(sm, logmag, phase, frame_offs[u], T, h0 - 2);
   const long long n_out = out_offs[u + 1] - out_offs[u];   // (T - 1) * 160 + 400
   const float scale = (float)((double)peak[u] + 0.000001);
   for (int i = threadIdx.x; i < kOH * kHop; i += blockDim.x) {
-    const int hl = i / kHop, r = i - hl * kHop;             // local hop, offset in hop
-    const long long n = (long long)(h0 + hl) * kHop + r;
+    const long long n = (long long)h0 * kHop + i;
     if (n >= n_out) continue;
-    // frame local index f = hl + 2 - j covers sample offset r + 160 j, j = 0..2 (zero frames outside [0, T))
-    float acc = s_y[(hl + 2) * kWin + r] + s_y[(hl + 1) * kWin + r + kHop];
-    if (r + 2 * kHop < kWin) acc += s_y[hl * kWin + r + 2 * kHop];
+    const float acc = ola_sample(s_y, i);
     const long long o = out_offs[u] + n;
     if (out_f32) out_f32[o] = acc;
     if (out_i16) {
@@ -184,6 +206,78 @@ istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, 
       out_i16[o] = (int16_t)__float2int_rn(v);
     }
   }
+}
+
+// Post-mix outputs of apply_snc (SN/apply.py:456-464) fused into one pass: both inverse STFTs (denoised
+// spectrum and the input spectrum = 'mixed_processed'), removed = mixed_processed - denoised, and the two
+// per-clip energy sums of snr_est = mean(denoised^2) / mean(removed^2).
+__global__ void __launch_bounds__(kThreads)
+istft_post_kernel(const float* __restrict__ den_logmag, const float* __restrict__ mix_logmag, const float* __restrict__ phase,
+                  const long long* __restrict__ frame_offs, const long long* __restrict__ out_offs,
+                  float* __restrict__ den_f32, float* __restrict__ mixed_f32, float* __restrict__ removed_f32,
+                  double* __restrict__ sums /* [U][2] */) {
+  __shared__ IstftSmem sm;
+  __shared__ float s_red[2][kThreads / 32];
+  const int u = blockIdx.y;
+  const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
+  if (T <= 0) return;
+  const int h0 = blockIdx.x * kOH;
+  if (h0 >= T + 2) return;
+  istft_load_tables(sm);
+  constexpr int PER = (kOH * kHop + kThreads - 1) / kThreads;
+  float den[PER];
+  const float* s_y = istft_frames(sm, den_logmag, phase, frame_offs[u], T, h0 - 2);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = threadIdx.x + k * kThreads;
+    den[k] = i < kOH * kHop ? ola_sample(s_y, i) : 0.f;
+  }
+  s_y = istft_frames(sm, mix_logmag, phase, frame_offs[u], T, h0 - 2);
+  const long long n_out = out_offs[u + 1] - out_offs[u];
+  float e_den = 0.f, e_rem = 0.f;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = threadIdx.x + k * kThreads;
+    const long long n = (long long)h0 * kHop + i;
+    if (i >= kOH * kHop || n >= n_out) continue;
+    const float mixed = ola_sample(s_y, i);
+    const float rem = mixed - den[k];                   // SN/apply.py:460
+    const long long o = out_offs[u] + n;
+    if (den_f32) den_f32[o] = den[k];
+    if (mixed_f32) mixed_f32[o] = mixed;
+    if (removed_f32) removed_f32[o] = rem;
+    e_den += den[k] * den[k];
+    e_rem += rem * rem;
+  }
+  for (int o = 16; o; o >>= 1) {
+    e_den += __shfl_xor_sync(0xffffffffu, e_den, o);
+    e_rem += __shfl_xor_sync(0xffffffffu, e_rem, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = e_den; s_red[1][threadIdx.x >> 5] = e_rem; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+    atomicAdd(&sums[2 * u], a);
+    atomicAdd(&sums[2 * u + 1], b);
+  }
+}
+
+// compensated = denoised + removed * factor, factor = snr_est / 20 (--ac) or the --compensate constant
+// (SN/apply.py:466-470); also writes snr_est[u].
+__global__ void compensate_kernel(const float* __restrict__ den, const float* __restrict__ removed,
+                                  const long long* __restrict__ out_offs, const double* __restrict__ sums, float compensate, int ac,
+                                  float* __restrict__ out, float* __restrict__ snr_est) {
+  const int u = blockIdx.y;
+  const long long b = out_offs[u], n = out_offs[u + 1] - b;
+  // both means share the sample count, so snr_est is the ratio of the sums
+  const double snr = sums[2 * u + 1] > 0 ? sums[2 * u] / sums[2 * u + 1] : INFINITY;
+  float factor = ac ? (float)(snr / 20.0) : compensate;
+  if (!isfinite(factor)) factor = 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && snr_est) snr_est[u] = (float)snr;
+  if (!out) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[b + i] = den[b + i] + removed[b + i] * factor;
 }
 
 }  // namespace
@@ -243,6 +337,26 @@ cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + 2 + kOH - 1) / kOH, U);
   istft_kernel<<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_istft_post(cudaStream_t s, const float* den_logmag, const float* mix_logmag, const float* phase,
+                              const long long* frame_offs, const long long* out_offs, int U, int max_frames_per_clip,
+                              float* den_f32, float* mixed_f32, float* removed_f32, double* sums) {
+  if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * U, s);
+  if (e != cudaSuccess) return e;
+  dim3 grid((max_frames_per_clip + 2 + kOH - 1) / kOH, U);
+  istft_post_kernel<<<grid, kThreads, 0, s>>>(den_logmag, mix_logmag, phase, frame_offs, out_offs, den_f32, mixed_f32,
+                                              removed_f32, sums);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compensate(cudaStream_t s, const float* den, const float* removed, const long long* out_offs, int U,
+                              const double* sums, float compensate, int ac, float* out, float* snr_est) {
+  if (U <= 0) return cudaSuccess;
+  dim3 grid(64, U);
+  compensate_kernel<<<grid, 256, 0, s>>>(den, removed, out_offs, sums, compensate, ac, out, snr_est);
   return cudaGetLastError();
 }
 

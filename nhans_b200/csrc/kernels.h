@@ -113,6 +113,12 @@ cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* off
 cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase, const long long* frame_offs,
                          const long long* out_offs, int U, const int* peak, long long total_blocks_hint,
                          int max_frames_per_clip, float* out_f32, int16_t* out_i16);
+// apply_snc post-mix outputs (SN/apply.py:456-470): both iSTFTs, removed, energy sums; then compensated / snr_est
+cudaError_t launch_istft_post(cudaStream_t s, const float* den_logmag, const float* mix_logmag, const float* phase,
+                              const long long* frame_offs, const long long* out_offs, int U, int max_frames_per_clip,
+                              float* den_f32, float* mixed_f32, float* removed_f32, double* sums);
+cudaError_t launch_compensate(cudaStream_t s, const float* den, const float* removed, const long long* out_offs, int U,
+                              const double* sums, float compensate, int ac, float* out, float* snr_est);
 cudaError_t dsp_init_tables();
 
 }  // namespace nhans

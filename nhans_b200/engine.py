@@ -187,6 +187,16 @@ class Engine:
             res["mixed_processed"] = unpack(mp, oo)
         return res
 
+    def postmix(self, out_offs, compensate=0.0, ac=False):
+        """SN post-mix outputs of the batch just enhanced -> dict of per-utterance lists + snr_est array."""
+        n, U = int(out_offs[-1]), len(out_offs) - 1
+        mixed, removed, comp = (np.zeros(n, np.float32) for _ in range(3))
+        snr = np.zeros(U, np.float32)
+        self._ck(self.lib.nhans_postmix(self.h, float(compensate), int(bool(ac)), _ptr(mixed), _ptr(removed), _ptr(comp), _ptr(snr)))
+        self.sync()
+        return {"mixed_processed": unpack(mixed, out_offs), "removed": unpack(removed, out_offs),
+                "compensated": unpack(comp, out_offs), "snr_est": snr}
+
     def upload(self, mix, mix_offs, ctx_a, a_offs, ctx_b, b_offs):
         self._ck(self.lib.nhans_upload(self.h, _ptr(mix), _ptr(mix_offs), len(mix_offs) - 1, _ptr(ctx_a), _ptr(a_offs),
                                        _ptr(ctx_b), _ptr(b_offs)))

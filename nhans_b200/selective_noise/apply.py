@@ -92,24 +92,19 @@ def apply_snc_batch(mixedpaths, pospaths, negpaths, save_tos, compensate=None, a
     negs = [read_wav(p) for p in negpaths]
     all_silent = all(_is_silent(p) for p in pospaths)
     poss = None if all_silent else [read_wav(p) for p in pospaths]
-    res = eng.enhance(mixes, poss, negs, want_f32=True, want_i16=False, want_mixproc=True)
+    res = eng.enhance(mixes, poss, negs, want_f32=True, want_i16=False)
+    # removed / snr_est / compensated (SN/apply.py:459-470) come from one fused GPU pass over the batch
+    post = eng.postmix(res["out_offs"], compensate=compensate, ac=ac)
     snrs = []
     for u, save_to in enumerate(save_tos):
-        den = res["f32"][u]
-        mixed = res["mixed_processed"][u]
         peak = float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0
-        _emit(save_to, den, peak, as_f32)
-        _emit(_sibling(save_to, "mixed_processed.wav"), mixed, peak, as_f32)
-        removed = mixed - den                                            # SN/apply.py:460
-        _emit(_sibling(save_to, "removed.wav"), removed, peak, as_f32)
-        denom = float(np.mean(np.square(removed))) if len(removed) else 0.0
-        snr_est = float(np.mean(np.square(den))) / denom if denom > 0 else float("inf")   # SN/apply.py:463
+        _emit(save_to, res["f32"][u], peak, as_f32)
+        _emit(_sibling(save_to, "mixed_processed.wav"), post["mixed_processed"][u], peak, as_f32)
+        _emit(_sibling(save_to, "removed.wav"), post["removed"][u], peak, as_f32)
+        snr_est = float(post["snr_est"][u])
         print(snr_est)
         print("---------------------------")
-        factor = snr_est / 20 if ac else compensate                      # SN/apply.py:466-469
-        if not np.isfinite(factor):
-            factor = 0.0
-        _emit(_sibling(save_to, "compensated.wav"), den + removed * factor, peak, as_f32)
+        _emit(_sibling(save_to, "compensated.wav"), post["compensated"][u], peak, as_f32)
         snrs.append(snr_est)
     return snrs
 

@@ -141,3 +141,20 @@ def test_cli_file_surface(tmp_path, monkeypatch):
     rate, y = read(str(d / "sep_denoised.wav"))
     assert rate == 16000 and y.dtype == np.float32                    # the reference's own output format
     session.close_all()
+
+
+def test_postmix_outputs_vs_oracle(engine_sn, oracle_sn):
+    """SN/apply.py:456-470 on the GPU (fused dual iSTFT + energy sums): removed, snr_est, compensated."""
+    mixes = [synth.mixture(0.6, 2), synth.mixture(0.4, 3)]
+    negs = [synth.noise_clip(2), synth.noise_clip(3)]
+    res = engine_sn.enhance(mixes, None, negs)
+    for ac, comp in ((False, 0.3), (True, 0.0)):
+        post = engine_sn.postmix(res["out_offs"], compensate=comp, ac=ac)
+        for u in range(2):
+            r = O.apply_arrays(oracle_sn, mixes[u], synth.silence(), negs[u], return_all=True)
+            removed, snr_est, compensated = O.post_mix(r["samples"], r["mixed_processed"], comp, ac)
+            assert np.abs(post["mixed_processed"][u] - r["mixed_processed"]).max() < 1e-5
+            assert _snr(removed, post["removed"][u]) >= 30.0          # removed is a small difference of two signals
+            assert abs(post["snr_est"][u] - snr_est) <= 5e-3 * abs(snr_est)
+            assert _snr(compensated, post["compensated"][u]) >= SNR_MIN_DB
+            assert np.abs(post["removed"][u] - (post["mixed_processed"][u] - res["f32"][u])).max() < 1e-5
