@@ -51,7 +51,7 @@ struct GemmLayerDev {
   KGroupDev* groups = nullptr;
   float *bias = nullptr, *tftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
   uint16_t *ttab16 = nullptr, *ftab16 = nullptr;
-  CUtensorMap mapA0, mapA1, mapB;
+  CUtensorMap mapA0, mapA1, mapB, mapBhalf;
 };
 
 struct NetDev {
@@ -218,6 +218,7 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
       if ((rc = make_map(ctx, a == 0 ? &D.mapA0 : &D.mapA1, net.bufs[buf], rowlen, elems / rowlen, 136))) return rc;
     }
     if ((rc = make_map(ctx, &D.mapB, D.w, L.K, L.N, L.BN))) return rc;
+    if ((rc = make_map(ctx, &D.mapBhalf, D.w, L.K, L.N, L.BN % 32 == 0 ? L.BN / 2 : L.BN))) return rc;   // CTA pairs load half of B each
   }
   const int cap = P.capacity;
   for (int** p : {&net.u_frame, &net.u_lo, &net.u_hi, &net.u_utt}) {
@@ -352,7 +353,11 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
     g.debug_stats = ctx->debug_stats ? ctx->debug_stats + 8 * ((&net == &ctx->tower ? 64 : 0) + (int)i) : nullptr;
     ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0, (&net == &ctx->tower ? 64 : 0) + (int)i);
-    CK(launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, g, ctx->desc_mode));
+    {
+      cudaError_t le = launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, D.mapBhalf, g, ctx->desc_mode);
+      if (le != cudaSuccess)
+        return fail(ctx, NHANS_ERR_CUDA, "launch of layer " + L.name + " (M " + std::to_string(g.M) + ", BN " + std::to_string(g.BN) + "): " + cudaGetErrorString(le));
+    }
   }
   return 0;
 }

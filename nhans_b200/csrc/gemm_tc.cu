@@ -23,6 +23,8 @@
 //
 // The epilogue is the fusion of blocks.py:104-108 (batch-norm), main.py:166,172 (conditioning adds),
 // main.py:184-186 (residual add, ReLU) folded as in SURVEY.md App. A.6.
+#include <cstdio>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -63,12 +65,14 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // MMA issuer (one warp): walks tiles / groups / sub-tiles in the producers' order; one elected lane issues
 // tcgen05.mma.  IL sub-tiles are processed together so that consecutive MMAs target different TMEM
 // accumulators (back-to-back MMAs into the same accumulator serialise on the accumulate dependency).
-template <int IL>
+template <int IL, bool CTA2>
 __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const GemmCfg& cfg, uint8_t* smem_a, uint8_t* smem_b,
                                            uint32_t tmem_base, int num_tiles, int b_bytes) {
+  const int cta_shift = CTA2 ? 1 : 0;
   const int MT = cfg.mt;
   const int num_groups = p.num_groups;
-  const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.BN);
+  // CTA pairs: M = 256 (bit 24.. holds M >> 4), issued by the leader for both CTAs
+  const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.BN) + (CTA2 ? (8u << 24) : 0u);
   const uint64_t desc_hi = ptx::umma_desc_sw128(0, 0);             // everything but the address field
   const uint32_t a_base = ptx::smem_u32(smem_a) >> 4, b_base = ptx::smem_u32(smem_b) >> 4;
   const uint32_t b_step = (uint32_t)b_bytes >> 4;
@@ -76,7 +80,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   bool b_ready = false;                                             // resident weights have landed
   long long w_tmem = 0, w_a = 0, w_b = 0;
   const long long t_start = clock64();
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+  for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
     ptx::mbar_wait_timed(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2, &w_tmem);
     ptx::tc_fence_after();
@@ -106,17 +110,21 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                         // +32 B inside the swizzle atom per K = 16
 #pragma unroll
-              for (int ii = 0; ii < IL; ++ii)
-                ptx::umma_f16(d_tm[ii], (desc_hi | (a_lo[ii] + sh)) + 2 * k, db + 2 * k, idesc, k == 0 ? first : 1u);
+              for (int ii = 0; ii < IL; ++ii) {
+                if (CTA2) ptx::umma_f16_2sm(d_tm[ii], (desc_hi | (a_lo[ii] + sh)) + 2 * k, db + 2 * k, idesc, k == 0 ? first : 1u);
+                else ptx::umma_f16(d_tm[ii], (desc_hi | (a_lo[ii] + sh)) + 2 * k, db + 2 * k, idesc, k == 0 ? first : 1u);
+              }
             }
-            if (i0 + IL >= MT && !cfg.resident) ptx::umma_commit(&ctrl->b_empty[bslot]);
+            if (i0 + IL >= MT && !cfg.resident) {
+              if (CTA2) ptx::umma_commit_2sm(&ctrl->b_empty[bslot]); else ptx::umma_commit(&ctrl->b_empty[bslot]);
+            }
           }
           __syncwarp();
           if (!cfg.resident && ++bslot == (uint32_t)cfg.nb) { bslot = 0; bphase ^= 1; }
         }
 #pragma unroll
         for (int ii = 0; ii < IL; ++ii) {
-          if (ptx::elect_one()) ptx::umma_commit(&ctrl->a_empty[aslot]);
+          if (ptx::elect_one()) { if (CTA2) ptx::umma_commit_2sm(&ctrl->a_empty[aslot]); else ptx::umma_commit(&ctrl->a_empty[aslot]); }
           __syncwarp();
           if (++aslot == (uint32_t)cfg.na) { aslot = 0; aphase ^= 1; }
         }
@@ -124,7 +132,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
       }
     }
     b_ready = true;
-    if (ptx::elect_one()) ptx::umma_commit(&ctrl->tmem_full[acc]);
+    if (ptx::elect_one()) { if (CTA2) ptx::umma_commit_2sm(&ctrl->tmem_full[acc]); else ptx::umma_commit(&ctrl->tmem_full[acc]); }
     __syncwarp();
   }
   if (p.debug_stats && (threadIdx.x & 31) == 0) {
@@ -147,10 +155,10 @@ constexpr int kEpiHead = 32;      // last_dense: fp32 out + centre frame
 // take alternate 16-column chunks.  Per chunk: tcgen05.ld (thread = row) -> XOR-swizzled 32 x 16 fp32 transpose
 // in shared memory -> 4 lanes per row x 4 channels, so that global loads / stores are coalesced.  The loads
 // of chunk k + 1 are in flight while chunk k is processed; slot metadata is computed one slot ahead.
-template <int EPI>
+template <int EPI, bool CTA2>
 __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, const GemmCfg& cfg, int ew, int lane,
                                               uint32_t tmem_base, int num_tiles, int n_tiles, const __half* s_ttab,
-                                              const __half* s_ftab) {
+                                              const __half* s_ftab, uint32_t rank) {
   constexpr bool kPair = EPI & kEpiPair, kRes = EPI & kEpiRes, kR1 = EPI & kEpiR1, kTabS = EPI & kEpiTabS,
                  kTabG = EPI & kEpiTabG, kHead = EPI & kEpiHead;
   const EpiDev& e = p.epi;
@@ -173,21 +181,30 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
   uint32_t it = 0;
   long long w_full = 0;
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+  const int cta_shift = CTA2 ? 1 : 0;   // CTA pairs: a sub-tile is 256 rows, this CTA owns rows [128 rank, +128)
+  const int sub_rows = 128 << cta_shift;
+  auto release_acc = [&](uint32_t acc) {      // one arrival per warp on the (leader's) accumulator-free barrier
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CTA2) ptx::mbar_arrive_cluster(&ctrl->tmem_empty[acc], 0);
+      else ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+    }
+  };
+  for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
     const int n0 = (tile % n_tiles) * p.BN;
     if (p.debug_skip_epilogue == 1) {
       ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+      release_acc(acc);
       continue;
     }
-    const int tile_m0 = (tile / n_tiles) * (MT * 128);
+    const int tile_m0 = (tile / n_tiles) * (MT * sub_rows) + (int)rank * 128;
     // metadata of the row this thread owns in slot v (its TMEM lane)
     auto slot_meta = [&](int v) -> int4 {
       if (v >= NV) return make_int4(-1, 0, 0, 0);
       const int i = kPair ? (v >> 1) : v, j = kPair ? (v & 1) : 0;
-      const int m = tile_m0 + i * 128 + q * 32 + lane;
+      const int m = tile_m0 + i * sub_rows + q * 32 + lane;
       if (m >= p.M) return make_int4(-1, 0, 0, 0);
       const int unit = m / hw;
       const int rem = m - unit * hw;
@@ -221,7 +238,7 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
 #pragma unroll 1
     for (int v = 0; v < NV; ++v) {
       const int i = kPair ? (v >> 1) : v;
-      const int m0 = tile_m0 + i * 128;
+      const int m0 = tile_m0 + i * sub_rows;
       if (m0 >= p.M) break;
       const int4 md_cur = md_next;
       md_next = slot_meta(v + 1);             // its loads are in flight while slot v is processed
@@ -340,20 +357,21 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
       }
     }
     if (!waited) ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
-    ptx::tc_fence_before();
-    ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+    release_acc(acc);
   }
   if (p.debug_stats && ew == 0 && lane == 0) atomicAdd(p.debug_stats + 3, (unsigned long long)w_full);
 }
 
-template <int EPI>
+template <int EPI, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const GemmDev p, const GemmCfg cfg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  const int b_bytes = p.BN * 128;
+  const int cta_shift = CTA2 ? 1 : 0;
+  const uint32_t rank = CTA2 ? ptx::cluster_ctarank() : 0u;     // CTA pairs: rank 0 (leader) issues the MMAs
+  const int b_bytes = (p.BN >> cta_shift) * 128;                     // a pair splits B: each CTA holds BN / 2 rows
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + cfg.na * kSlabBytes;
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_b + (size_t)cfg.nb * b_bytes);
@@ -362,7 +380,8 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int MT = cfg.mt;                          // sub-tiles of 128 rows per CTA tile
   const int n_tiles = p.N / p.BN;
-  const int m_tiles = (p.M + MT * 128 - 1) / (MT * 128);
+  const int tile_rows = (MT * 128) << cta_shift;
+  const int m_tiles = (p.M + tile_rows - 1) / tile_rows;
   const int num_tiles = m_tiles * n_tiles;
   const int num_groups = p.num_groups;
 
@@ -381,7 +400,7 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     for (int s = 0; s < cfg.nb; ++s) { ptx::mbar_init(&ctrl->b_full[s], 1); ptx::mbar_init(&ctrl->b_empty[s], 1); }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&ctrl->tmem_full[a], 1);
-      ptx::mbar_init(&ctrl->tmem_empty[a], kEpiWarps * 32);
+      ptx::mbar_init(&ctrl->tmem_empty[a], kEpiWarps << cta_shift);       // one arrival per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -391,9 +410,10 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::tma_prefetch_desc(&mapA1);
     ptx::tma_prefetch_desc(&mapB);
   }
-  if (warp == kWarpMma) ptx::tmem_alloc(&ctrl->tmem_base, 512);
+  if (warp == kWarpMma) { if (CTA2) ptx::tmem_alloc_2sm(&ctrl->tmem_base, 512); else ptx::tmem_alloc(&ctrl->tmem_base, 512); }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CTA2) ptx::cluster_sync();          // the peer's barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
@@ -403,16 +423,23 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // ===================== A producer: one slab per (group, sub-tile) =====================
     // (whole warp runs the loop; one elected lane issues the TMA - keeps the control flow warp-uniform)
     uint32_t slot = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * (MT * 128);
+    for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift) {
+      const int m0 = (tile / n_tiles) * tile_rows + (int)rank * 128;
       for (int g = 0; g < num_groups; ++g) {
         const int row_off = ctrl->groups[g].row_off, col = ctrl->groups[g].col, map = ctrl->groups[g].map;
         for (int i = 0; i < MT; ++i) {
           ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&ctrl->a_full[slot], kSlabBytes);
-            ptx::tma_load_2d(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, &ctrl->a_full[slot], col,
-                             m0 + i * 128 + row_off);
+            if (CTA2) {
+              // both CTAs' slabs are credited to the leader's barrier
+              if (rank == 0) ptx::mbar_expect_tx(&ctrl->a_full[slot], 2 * kSlabBytes);
+              ptx::tma_load_2d_2sm(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, &ctrl->a_full[slot], col,
+                                   m0 + i * 256 + row_off);
+            } else {
+              ptx::mbar_expect_tx(&ctrl->a_full[slot], kSlabBytes);
+              ptx::tma_load_2d(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, &ctrl->a_full[slot], col,
+                               m0 + i * 128 + row_off);
+            }
           }
           __syncwarp();
           if (++slot == (uint32_t)cfg.na) { slot = 0; phase ^= 1; }
@@ -432,16 +459,21 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     } else {
       uint32_t slot = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles) * p.BN;
+      for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift) {
+        const int n0 = (tile % n_tiles) * p.BN + (int)rank * (p.BN >> 1) * cta_shift;
         for (int g = 0; g < num_groups; ++g) {
           const int ntaps = ctrl->groups[g].ntaps;
           for (int t = 0; t < ntaps; ++t) {
             const int bk = ctrl->groups[g].bk[t];
             ptx::mbar_wait(&ctrl->b_empty[slot], phase ^ 1, p.err_flag, 5);
             if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(&ctrl->b_full[slot], (uint32_t)b_bytes);
-              ptx::tma_load_2d(smem_b + (size_t)slot * b_bytes, &mapB, &ctrl->b_full[slot], bk * 64, n0);
+              if (CTA2) {
+                if (rank == 0) ptx::mbar_expect_tx(&ctrl->b_full[slot], 2u * (uint32_t)b_bytes);
+                ptx::tma_load_2d_2sm(smem_b + (size_t)slot * b_bytes, &mapB, &ctrl->b_full[slot], bk * 64, n0);
+              } else {
+                ptx::mbar_expect_tx(&ctrl->b_full[slot], (uint32_t)b_bytes);
+                ptx::tma_load_2d(smem_b + (size_t)slot * b_bytes, &mapB, &ctrl->b_full[slot], bk * 64, n0);
+              }
             }
             __syncwarp();
             if (++slot == (uint32_t)cfg.nb) { slot = 0; phase ^= 1; }
@@ -451,28 +483,32 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
-    if (cfg.il == 4) mma_issuer<4>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
-    else if (cfg.il == 2) mma_issuer<2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
-    else mma_issuer<1>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+    if (rank != 0) {
+      // the peer CTA of a pair only lends its shared memory / TMEM; the leader issues for both
+    } else if (cfg.il == 4) mma_issuer<4, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+    else if (cfg.il == 2) mma_issuer<2, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+    else mma_issuer<1, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
   } else {
     // ===================== epilogue (warps 0..7) =====================
-    epilogue_warp<EPI>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab);
+    epilogue_warp<EPI, CTA2>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab, rank);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CTA2) ptx::cluster_sync();          // nobody exits while the partner may still signal / read it
   if (warp == kWarpMma) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (CTA2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
 }  // namespace
 
-int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, GemmCfg* cfg) {
-  const int b_bytes = BN * 128;
+int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, GemmCfg* cfg) {
+  const int b_bytes = (cta2 ? BN / 2 : BN) * 128;
   GemmCfg c;
+  c.cta2 = cta2;
   // shared-memory tables only where the epilogue is the critical path (short main loops: BN <= 128)
   c.tab_bytes = (BN <= 128 && tab_bytes > 0) ? ((tab_bytes + 127) & ~127) : 0;
   c.mt = 256 / BN < 1 ? 1 : 256 / BN;
@@ -480,7 +516,7 @@ int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, GemmCfg* cfg) {
   const int budget = kSmemLimit - 1024 - kCtrlBytes - kEpiBytes - c.tab_bytes - c.na * kSlabBytes;
   c.nb = budget / b_bytes;
   if (c.nb > kMaxB) c.nb = kMaxB;
-  c.resident = (num_kb <= c.nb) ? 1 : 0;
+  c.resident = (num_kb <= c.nb && !cta2) ? 1 : 0;
   c.desc_mode = 0;
   c.il = c.mt >= 2 ? 2 : 1;
   if (cfg) *cfg = c;
@@ -488,15 +524,37 @@ int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, GemmCfg* cfg) {
 }
 
 namespace {
-template <int EPI>
+template <int EPI, bool CTA2>
 cudaError_t launch_flavour(cudaStream_t s, int grid, int smem, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const GemmDev& p, const GemmCfg& cfg) {
+  if (CTA2) {
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_shift_kernel<EPI, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e2 != cudaSuccess) return e2;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kGemmThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&lc, gemm_shift_kernel<EPI, CTA2>, a0, a1, b, p, cfg);
+    if (le != cudaSuccess) {
+      int nclusters = -1;
+      cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, gemm_shift_kernel<EPI, CTA2>, &lc);
+      fprintf(stderr, "nhans: cluster launch failed (%s): grid %d, smem %d, max active clusters %d (%s)\n", cudaGetErrorString(le), grid, smem,
+              nclusters, cudaGetErrorString(oe));
+    }
+    return le;
+  }
   static bool configured = false;           // per process; every device of one box runs the same binary
-  cudaError_t e = cudaFuncSetAttribute(gemm_shift_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  cudaError_t e = cudaFuncSetAttribute(gemm_shift_kernel<EPI, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   if (e != cudaSuccess) return e;
   configured = true;
   (void)configured;
-  gemm_shift_kernel<EPI><<<grid, kGemmThreads, smem, s>>>(a0, a1, b, p, cfg);
+  gemm_shift_kernel<EPI, CTA2><<<grid, kGemmThreads, smem, s>>>(a0, a1, b, p, cfg);
   return cudaGetLastError();
 }
 }  // namespace
@@ -504,18 +562,23 @@ cudaError_t launch_flavour(cudaStream_t s, int grid, int smem, const CUtensorMap
 cudaError_t gemm_configure() { return cudaSuccess; }
 
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
-                        const CUtensorMap& mapB, const GemmDev& p, int desc_mode) {
+                        const CUtensorMap& mapB_full, const CUtensorMap& mapB_half, const GemmDev& p, int desc_mode) {
   if (p.M <= 0) return cudaSuccess;
   if (p.num_groups > kMaxGroups || p.BN % 16 != 0 || p.BN > 256 || p.N % p.BN != 0) return cudaErrorInvalidValue;
   GemmCfg cfg;
   const int tab_bytes = (p.epi.ttab16 && p.epi.ftab16) ? (p.epi.tab_H + p.epi.tab_W) * (p.epi.pair ? p.epi.n_real : p.N) * 2 : 0;
-  const int smem = gemm_smem_bytes(p.BN, p.num_kb, tab_bytes, &cfg);
+  // CTA pairs whenever there is enough work for every pair and B splits into two legal boxes (debug: bit 4 of desc_mode disables)
+  const int cta2 = (!(desc_mode & 16) && (p.BN % 32) == 0 && !p.epi.head && p.M >= 256 * (n_sm / 2)) ? 1 : 0;
+  const int smem = gemm_smem_bytes(p.BN, p.num_kb, tab_bytes, cta2, &cfg);
+  const CUtensorMap& mapB = cta2 ? mapB_half : mapB_full;
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
-  if (desc_mode >> 1) { cfg.il = desc_mode >> 1; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
+  if ((desc_mode >> 1) & 7) { cfg.il = (desc_mode >> 1) & 7; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
   if (cfg.nb < 4) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight
-  const int tiles = ((p.M + cfg.mt * 128 - 1) / (cfg.mt * 128)) * (p.N / p.BN);
-  const int grid = tiles < n_sm ? tiles : n_sm;
+  const int tile_rows = (cfg.mt * 128) << cta2;
+  const int tiles = ((p.M + tile_rows - 1) / tile_rows) * (p.N / p.BN);
+  int grid = tiles < (n_sm >> cta2) ? tiles : (n_sm >> cta2);
+  grid <<= cta2;                              // CTA pairs: two CTAs per tile
   const EpiDev& e = p.epi;
   int fl = 0;
   if (e.head) fl = kEpiHead;
@@ -525,7 +588,9 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
     if (e.r1_vec) fl |= kEpiR1;
     if (e.tftab) fl |= cfg.tab_bytes ? kEpiTabS : kEpiTabG;
   }
-#define NHANS_FLAVOUR(F) case F: return launch_flavour<F>(s, grid, smem, mapA0, mapA1, mapB, p, cfg);
+#define NHANS_FLAVOUR(F) \
+  case F:                \
+    return cta2 ? launch_flavour<F, true>(s, grid, smem, mapA0, mapA1, mapB, p, cfg) : launch_flavour<F, false>(s, grid, smem, mapA0, mapA1, mapB, p, cfg);
   switch (fl) {
     NHANS_FLAVOUR(0)                                   // tower conv1 / conv2 with GEMM transform, last_conv
     NHANS_FLAVOUR(kEpiR1)                              // tower block-1 conv2
