@@ -57,6 +57,11 @@ int nhans_normalise(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int
 int nhans_stft(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int U, float* logmag, float* phase,
                int64_t* frame_offs, int32_t* peak);
 
+/* The same transform of float32 samples that are already normalised / mixed (apply_demo, SN/apply.py:241-251:
+ * the on-the-fly mixture and the scaled noise signals returned by combine_signals).  No peak normalisation. */
+int nhans_stft_f32(nhans_ctx* ctx, const float* x, const int64_t* offs, int U, float* logmag, float* phase,
+                   int64_t* frame_offs);
+
 /* Embedding tower (SN/main.py:189-202): ctx_logmag [R][200][201] -> emb [R][512]. */
 int nhans_embed(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb);
 

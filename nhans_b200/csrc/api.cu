@@ -59,6 +59,7 @@ struct NetDev {
   std::vector<__half*> bufs;
   std::vector<GemmLayerDev> layers;
   float *first_w = nullptr, *first_bias = nullptr, *first_tftab = nullptr;
+  uint16_t *first_ttab16 = nullptr, *first_ftab16 = nullptr;
   float *Pa = nullptr, *Pb = nullptr, *c = nullptr;
   int *u_frame = nullptr, *u_lo = nullptr, *u_hi = nullptr, *u_utt = nullptr;
   std::vector<void*> allocs;
@@ -180,6 +181,8 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
   if ((rc = upload(ctx, net, P.first.w, &net.first_w))) return rc;
   if ((rc = upload(ctx, net, P.first.epi.bias, &net.first_bias))) return rc;
   if ((rc = upload(ctx, net, P.first.epi.tftab, &net.first_tftab))) return rc;
+  if ((rc = upload(ctx, net, P.first.epi.ttab16, &net.first_ttab16))) return rc;
+  if ((rc = upload(ctx, net, P.first.epi.ftab16, &net.first_ftab16))) return rc;
   if ((rc = upload(ctx, net, P.cond.Pa, &net.Pa))) return rc;
   if ((rc = upload(ctx, net, P.cond.Pb, &net.Pb))) return rc;
   if ((rc = upload(ctx, net, P.cond.c, &net.c))) return rc;
@@ -331,6 +334,9 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     d.w = net.first_w;
     d.units_tab = ut;
     d.epi = make_epi(net, D.epi, D.out, net.first_bias, net.first_tftab, nullptr, nullptr, raw, cond_table, nullptr);
+    d.epi.ttab16 = reinterpret_cast<const __half*>(net.first_ttab16);
+    d.epi.ftab16 = reinterpret_cast<const __half*>(net.first_ftab16);
+    d.epi.tab_H = D.Ho; d.epi.tab_W = D.Wo;
     ProfScope ps(ctx, 3, 2.0 * D.macs_per_unit * units, 0);
     CK(launch_direct_conv(ctx->stream, d));
   }
@@ -598,6 +604,40 @@ int nhans_stft(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int U, f
   if (logmag) CK(cudaMemcpyAsync(logmag, ctx->tmp[4].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (phase) CK(cudaMemcpyAsync(phase, ctx->tmp[5].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (peak) CK(cudaMemcpyAsync(peak, ctx->tmp[3].p, sizeof(int) * U, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NHANS_OK;
+}
+
+int nhans_stft_f32(nhans_ctx* ctx, const float* x, const int64_t* offs, int U, float* logmag, float* phase,
+                   int64_t* frame_offs) {
+  if (!ctx || !x || !offs || !frame_offs || U <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<long long> rel(U + 1), fo(U + 1, 0);
+  int max_frames = 0;
+  for (int u = 0; u <= U; ++u) rel[u] = offs[u] - offs[0];
+  for (int u = 0; u < U; ++u) {
+    int T = frames_of(offs[u + 1] - offs[u]);
+    max_frames = std::max(max_frames, T);
+    fo[u + 1] = fo[u] + T;
+  }
+  for (int u = 0; u <= U; ++u) frame_offs[u] = fo[u];
+  if (!logmag && !phase) return NHANS_OK;
+  const long long total = rel[U];
+  CK(ctx->tmp[0].ensure(total * 4 + 8));
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, x + offs[0], total * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[1], rel))) return rc;
+  if ((rc = to_device_offs(ctx, ctx->tmp[2], fo))) return rc;
+  const size_t sbytes = (size_t)fo[U] * kBins * 4;
+  CK(ctx->tmp[4].ensure(sbytes + 4));
+  CK(ctx->tmp[5].ensure(sbytes + 4));
+  {
+    ProfScope ps(ctx, 1, 0, 4.0 * total + 2.0 * sbytes);
+    CK(launch_stft_f32(ctx->stream, ctx->tmp[0].as<float>(), ctx->tmp[1].as<long long>(), ctx->tmp[2].as<long long>(), U,
+                       max_frames, ctx->tmp[4].as<float>(), ctx->tmp[5].as<float>()));
+  }
+  if (logmag) CK(cudaMemcpyAsync(logmag, ctx->tmp[4].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (phase) CK(cudaMemcpyAsync(phase, ctx->tmp[5].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return NHANS_OK;
 }

@@ -65,8 +65,9 @@ __global__ void peak_kernel(const int16_t* __restrict__ pcm, const long long* __
 
 // grid: (ceil(max_frames / kFB), U)
 __global__ void __launch_bounds__(kThreads)
-stft_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ offs, const long long* __restrict__ frame_offs,
-            const int* __restrict__ peak, float* __restrict__ logmag, float* __restrict__ phase) {
+stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const long long* __restrict__ offs,
+            const long long* __restrict__ frame_offs, const int* __restrict__ peak, float* __restrict__ logmag,
+            float* __restrict__ phase) {
   __shared__ float s_x[(kFB - 1) * kHop + kWin];
   __shared__ float2 s_a[kFB * 200];
   __shared__ float2 s_b[kFB * 200];
@@ -79,8 +80,12 @@ stft_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ offs,
   const int nf = min(kFB, T - t0);
   const long long base = offs[u] + (long long)t0 * kHop;
   const int span = (nf - 1) * kHop + kWin;
-  const double denom = (double)peak[u] + 0.000001;
-  for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)pcm[base + i] / denom);
+  if (xf) {                              // already-normalised float samples (apply_demo, SN/apply.py:241-247)
+    for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = xf[base + i];
+  } else {
+    const double denom = (double)peak[u] + 0.000001;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)pcm[base + i] / denom);
+  }
   for (int i = threadIdx.x; i < 200; i += blockDim.x) s_tw200[i] = g_tw200[i];
   for (int i = threadIdx.x; i < 201; i += blockDim.x) s_tw400[i] = g_tw400[i];
   __syncthreads();
@@ -318,7 +323,15 @@ cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* off
   (void)total_frames;
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
-  stft_kernel<<<grid, kThreads, 0, s>>>(pcm, offs, frame_offs, peak, logmag, phase);
+  stft_kernel<<<grid, kThreads, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stft_f32(cudaStream_t s, const float* x, const long long* offs, const long long* frame_offs, int U,
+                            int max_frames_per_clip, float* logmag, float* phase) {
+  if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
+  dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
+  stft_kernel<<<grid, kThreads, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
   return cudaGetLastError();
 }
 

@@ -127,13 +127,27 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 
 constexpr int kMmaWarps = 4;
 constexpr int kMmaPitch = 68;                          // floats per staged pixel row
+// A warp walks one output image row (unit, ho) in 16-pixel segments, so everything that depends on the row only -
+// the frame bounds, the per-utterance bias, the time-embedding row T[ho] folded into it, the output row address - is
+// set up once per 13 segments; per pixel only the frequency-embedding row F[wo] (fp16, 25 KB, L1 resident) is read.
+// kTab: 0 = no tables (tower), 1 = separable fp16 tables, 2 = combined fp32 table (fallback).
+__device__ __forceinline__ void add_half8(float (&b)[8], const uint4 t) {
+  const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    b[2 * i] += f.x;
+    b[2 * i + 1] += f.y;
+  }
+}
+
+template <int KSTEPS>
 __global__ void __launch_bounds__(kMmaWarps * 32)
 direct_conv_mma_kernel(const DirectDev p, const int segs) {
   extern __shared__ float4 s_b[];                      // [ksteps][8 n-tiles][32 lanes] {b0_hi, b1_hi, b0_lo, b1_lo}
-  const int ksteps = p.kh / 2;                         // 8 taps (two kernel rows of width 4) per k-step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* st = reinterpret_cast<float*>(s_b + ksteps * 8 * 32) + warp * 16 * kMmaPitch;
-  for (int idx = threadIdx.x; idx < ksteps * 8 * 32; idx += blockDim.x) {
+  float* st = reinterpret_cast<float*>(s_b + KSTEPS * 8 * 32) + warp * 16 * kMmaPitch;
+  for (int idx = threadIdx.x; idx < KSTEPS * 8 * 32; idx += blockDim.x) {
     const int l = idx & 31, nt = (idx >> 5) & 7, ks = idx >> 8;
     const int n = nt * 8 + (l >> 2);                   // B fragment: b0 = (k = l % 4, n), b1 = (k + 4, n)
     const float w0 = p.w[(ks * 8 + (l & 3)) * 64 + n], w1 = p.w[(ks * 8 + (l & 3) + 4) * 64 + n];
@@ -142,86 +156,104 @@ direct_conv_mma_kernel(const DirectDev p, const int segs) {
   }
   __syncthreads();
   const EpiDev& e = p.epi;
-  const long long tiles = (long long)p.units * p.Ho * segs;
+  const int rows = p.units * p.Ho;
   const int g4 = lane >> 2, t4 = lane & 3;             // fragment row / column ids
   const int sub = lane >> 3, cg = (lane & 7) * 8;      // epilogue: 4 pixels per pass, 8 channels per lane
-  for (long long tile = (long long)blockIdx.x * kMmaWarps + warp; tile < tiles; tile += (long long)gridDim.x * kMmaWarps) {
-    const int seg = (int)(tile % segs);
-    const long long rowid = tile / segs;
-    const int ho = (int)(rowid % p.Ho), unit = (int)(rowid / p.Ho);
-    const int wo0 = seg * 16;
+  const int tab = (e.ttab16 && e.ftab16) ? 1 : (e.tftab ? 2 : 0);
+  const int xshift = e.o_sw == 1 ? 0 : (e.o_sw == 2 ? 1 : -1);
+  for (int rowid = blockIdx.x * kMmaWarps + warp; rowid < rows; rowid += gridDim.x * kMmaWarps) {
+    const int unit = rowid / p.Ho, ho = rowid - unit * p.Ho;
     const int frame0 = p.units_tab.frame[unit] + p.raw_oh;
     const int lo = p.units_tab.lo[unit], hi = p.units_tab.hi[unit];
-    float acc[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-    for (int ks = 0; ks < ksteps; ++ks) {
-      // A fragment: a0 = (px g4, tap t4), a1 = (px g4 + 8, tap t4), a2 = (px g4, tap t4 + 4), a3 = (px g4 + 8, tap t4 + 4)
-      float av[4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {                    // h: kernel row 2 ks + h  (taps t4 and t4 + 4)
-        const int r = ho * p.sh + 2 * ks + h - p.pt;
-        const int frame = frame0 + r;
-        const bool row_ok = r >= 0 && r < p.Hin && frame >= lo && frame < hi;
-        const float* row = e.raw + (size_t)frame * 201;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {                  // q: pixel g4 + 8 q
-          const int f = (wo0 + g4 + 8 * q) * p.sw + t4 - p.pl;
-          av[2 * h + q] = (row_ok && f >= 0 && f < p.Win) ? __ldg(row + f) : 0.f;
-        }
-      }
-      uint32_t a_hi[4], a_lo[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a_hi[k] = to_tf32(av[k]);
-        a_lo[k] = to_tf32(av[k] - __uint_as_float(a_hi[k]));
-      }
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const float4 b = s_b[(ks * 8 + nt) * 32 + lane];
-        mma_tf32(acc[nt], a_lo, __float_as_uint(b.x), __float_as_uint(b.y));
-        mma_tf32(acc[nt], a_hi, __float_as_uint(b.z), __float_as_uint(b.w));
-        mma_tf32(acc[nt], a_hi, __float_as_uint(b.x), __float_as_uint(b.y));
-      }
-    }
-    // C fragment -> staging: c0/c1 = (px g4, ch 8 nt + 2 t4 + {0,1}), c2/c3 = (px g4 + 8, ...)
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      *reinterpret_cast<float2*>(st + g4 * kMmaPitch + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
-      *reinterpret_cast<float2*>(st + (g4 + 8) * kMmaPitch + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
-    }
-    __syncwarp();
     const int utt = p.units_tab.utt ? p.units_tab.utt[unit] : 0;
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + (size_t)utt * e.bias_stride + cg);
-    const float4 bias0 = __ldg(b4), bias1 = __ldg(b4 + 1);
+    // source rows of the 2 KSTEPS kernel rows (null when the row is padding or another utterance's frame)
+    const float* src[2 * KSTEPS];
+#pragma unroll
+    for (int i = 0; i < 2 * KSTEPS; ++i) {
+      const int r = ho * p.sh + i - p.pt;
+      const int frame = frame0 + r;
+      src[i] = (r >= 0 && r < p.Hin && frame >= lo && frame < hi) ? e.raw + (size_t)frame * 201 : nullptr;
+    }
+    float bias[8];
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + (size_t)utt * e.bias_stride + cg);
+      const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+      if (tab == 1) add_half8(bias, __ldg(reinterpret_cast<const uint4*>(e.ttab16 + ho * 64 + cg)));
+    }
     const int yy = ho + e.o_oy;
     const long long row_pix = (long long)unit * e.o_Hq * e.o_Wq + (long long)(yy / e.o_sh) * e.o_Wq;
     const int plane_y = (yy % e.o_sh) * e.o_sw;
+    for (int seg = 0; seg < segs; ++seg) {
+      const int wo0 = seg * 16;
+      float acc[8][4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int px = g * 4 + sub, wo = wo0 + px;
-      if (wo >= p.Wo) continue;
-      const float4 a0 = *reinterpret_cast<const float4*>(st + px * kMmaPitch + cg);
-      const float4 a1 = *reinterpret_cast<const float4*>(st + px * kMmaPitch + cg + 4);
-      float4 b0 = bias0, b1 = bias1;
-      if (e.tftab) {
-        const float4* t4p = reinterpret_cast<const float4*>(e.tftab + ((size_t)ho * p.Wo + wo) * 64 + cg);
-        const float4 t0 = __ldg(t4p), t1 = __ldg(t4p + 1);
-        b0.x += t0.x; b0.y += t0.y; b0.z += t0.z; b0.w += t0.w;
-        b1.x += t1.x; b1.y += t1.y; b1.z += t1.z; b1.w += t1.w;
-      }
-      float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-      if (e.relu) {
+      for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+      const int f0 = (wo0 + g4) * p.sw + t4 - p.pl, f1 = f0 + 8 * p.sw;
+      const bool ok0 = f0 >= 0 && f0 < p.Win, ok1 = f1 >= 0 && f1 < p.Win;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        // A fragment: a0 = (px g4, tap t4), a1 = (px g4 + 8, tap t4), a2 = (px g4, tap t4 + 4), a3 = (px g4 + 8, tap t4 + 4)
+        float av[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                  // h: kernel row 2 ks + h  (taps t4 and t4 + 4)
+          const float* row = src[2 * ks + h];
+          av[2 * h] = (row && ok0) ? __ldg(row + f0) : 0.f;
+          av[2 * h + 1] = (row && ok1) ? __ldg(row + f1) : 0.f;
+        }
+        uint32_t a_hi[4], a_lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a_hi[k] = to_tf32(av[k]);
+          a_lo[k] = to_tf32(av[k] - __uint_as_float(a_hi[k]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float4 b = s_b[(ks * 8 + nt) * 32 + lane];
+          mma_tf32(acc[nt], a_lo, __float_as_uint(b.x), __float_as_uint(b.y));
+          mma_tf32(acc[nt], a_hi, __float_as_uint(b.z), __float_as_uint(b.w));
+          mma_tf32(acc[nt], a_hi, __float_as_uint(b.x), __float_as_uint(b.y));
+        }
       }
-      const int xx = wo + e.o_ox;
-      const long long pix = (long long)(plane_y + (xx % e.o_sw)) * e.o_plane + row_pix + (xx / e.o_sw);
-      uint4 o;
-      o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
-      o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(e.out + pix * e.out_C + cg) = o;
+      // C fragment -> staging: c0/c1 = (px g4, ch 8 nt + 2 t4 + {0,1}), c2/c3 = (px g4 + 8, ...)
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(st + g4 * kMmaPitch + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(st + (g4 + 8) * kMmaPitch + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int px = g * 4 + sub, wo = wo0 + px;
+        if (wo >= p.Wo) continue;
+        const float4 a0 = *reinterpret_cast<const float4*>(st + px * kMmaPitch + cg);
+        const float4 a1 = *reinterpret_cast<const float4*>(st + px * kMmaPitch + cg + 4);
+        float v[8] = {bias[0], bias[1], bias[2], bias[3], bias[4], bias[5], bias[6], bias[7]};
+        if (tab == 1) {
+          add_half8(v, __ldg(reinterpret_cast<const uint4*>(e.ftab16 + wo * 64 + cg)));
+        } else if (tab == 2) {
+          const float4* t4p = reinterpret_cast<const float4*>(e.tftab + ((size_t)ho * p.Wo + wo) * 64 + cg);
+          const float4 t0 = __ldg(t4p), t1 = __ldg(t4p + 1);
+          v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+          v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+        }
+        v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+        v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+        if (e.relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        const int xx = wo + e.o_ox;
+        long long pix;
+        if (xshift >= 0) pix = (long long)(plane_y + (xx & ((1 << xshift) - 1))) * e.o_plane + row_pix + (xx >> xshift);
+        else pix = (long long)(plane_y + (xx % e.o_sw)) * e.o_plane + row_pix + (xx / e.o_sw);
+        uint4 o;
+        o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+        o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(e.out + pix * e.out_C + cg) = o;
+      }
     }
   }
 }
@@ -305,13 +337,14 @@ __global__ void units_rows_kernel(int r0, int n_units, int rows, int* frame, int
 cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p) {
   if (p.units <= 0) return cudaSuccess;
   if (p.N != 64) return cudaErrorInvalidValue;
-  if (p.kw == 4 && (p.kh % 2) == 0 && !getenv("NHANS_DIRECT_FMA")) {
+  if (p.kw == 4 && p.kh == 4 && !getenv("NHANS_DIRECT_FMA")) {
     const int segs = (p.Wo + 15) / 16;
-    const long long tiles = (long long)p.units * p.Ho * segs;
-    const size_t smem_mma = (size_t)(p.kh / 2) * 8 * 32 * 16 + kMmaWarps * 16 * kMmaPitch * 4;
-    long long blocks_mma = (tiles + kMmaWarps - 1) / kMmaWarps;
-    if (blocks_mma > 148 * 32) blocks_mma = 148 * 32;              // grid-stride: the weight fragments are staged once per CTA
-    direct_conv_mma_kernel<<<(unsigned)blocks_mma, kMmaWarps * 32, smem_mma, s>>>(p, segs);
+    const long long rows = (long long)p.units * p.Ho;
+    if (rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const size_t smem_mma = (size_t)2 * 8 * 32 * 16 + kMmaWarps * 16 * kMmaPitch * 4;
+    long long blocks_mma = (rows + kMmaWarps - 1) / kMmaWarps;
+    if (blocks_mma > 148 * 16) blocks_mma = 148 * 16;              // grid-stride: the weight fragments are staged once per CTA
+    direct_conv_mma_kernel<2><<<(unsigned)blocks_mma, kMmaWarps * 32, smem_mma, s>>>(p, segs);
     return cudaGetLastError();
   }
   const long long total = (long long)p.units * p.Ho * p.Wo;

@@ -123,6 +123,42 @@ class Engine:
         self._ck(self.lib.nhans_stft(self.h, _ptr(data), _ptr(offs), U, _ptr(lm), _ptr(ph), _ptr(fo), _ptr(peak)))
         return lm, ph, fo, peak
 
+    def stft_f32(self, signals):
+        """float32 sample arrays (already normalised / mixed) -> (logmag [F,201], phase [F,201], frame_offs [U+1])"""
+        U = len(signals)
+        offs = np.zeros(U + 1, np.int64)
+        for i, c in enumerate(signals):
+            offs[i + 1] = offs[i] + len(c)
+        data = np.ascontiguousarray(np.concatenate([np.asarray(c, np.float32) for c in signals]))
+        fo = np.zeros(U + 1, np.int64)
+        self._ck(self.lib.nhans_stft_f32(self.h, _ptr(data), _ptr(offs), U, None, None, _ptr(fo)))
+        F = int(fo[-1])
+        lm = np.zeros((F, N_BINS), np.float32)
+        ph = np.zeros((F, N_BINS), np.float32)
+        self._ck(self.lib.nhans_stft_f32(self.h, _ptr(data), _ptr(offs), U, _ptr(lm), _ptr(ph), _ptr(fo)))
+        return lm, ph, fo
+
+    def enhance_demo(self, mix, sig_a, sig_b, start=CTX_FRAMES):
+        """apply_demo (SN/apply.py:247-337, SS/apply.py:198-285): float mixture + two float context signals.
+        Contexts are the first 200 frames of sig_a / sig_b, windows are taken over mix frames [start:] only (the
+        slice is zero padded like a whole utterance).  -> (denoised samples, mixture-centre samples)."""
+        lm, ph, fo = self.stft_f32([mix, sig_a, sig_b])
+        T = int(fo[1])
+        for u in (1, 2):
+            if fo[u + 1] - fo[u] < CTX_FRAMES:
+                raise NhansError(-4, "context signal yields %d < 200 STFT frames" % (fo[u + 1] - fo[u]))
+        if T <= start:
+            raise NhansError(-2, "the mixture has %d <= %d frames" % (T, start))
+        ctx = np.stack([lm[fo[1]:fo[1] + CTX_FRAMES], lm[fo[2]:fo[2] + CTX_FRAMES]])
+        emb = self.embed(ctx)
+        sl = np.ascontiguousarray(lm[start:T])
+        sp = np.ascontiguousarray(ph[start:T])
+        f1 = np.array([0, T - start], np.int64)
+        den = self.masknet(sl, f1, emb[0:1], emb[1:2])
+        y, _ = self.istft(den, sp, f1)
+        ymix, _ = self.istft(sl, sp, f1)
+        return y, ymix
+
     def embed(self, ctx_logmag):
         x = np.ascontiguousarray(ctx_logmag, np.float32).reshape(-1, CTX_FRAMES, N_BINS)
         emb = np.zeros((x.shape[0], 512), np.float32)

@@ -52,6 +52,70 @@ def handle_signals(mixedpath, noisepospath, noisenegpath):
     return pos, neg, mixed
 
 
+def _seq_sum(x):
+    # the reference uses the Python builtin sum() over a float32 array (SN/apply.py:77-79): a sequential
+    # accumulation that starts from int 0 and therefore runs in float64 under the numpy of its era
+    return float(np.cumsum(np.asarray(x, np.float64))[-1]) if len(x) else 0.0
+
+
+def _fit_noise(noise, n):
+    # SN/apply.py:57-72: repeat the noise until it covers the speech, or cut it
+    nse = noise
+    while n - len(nse) > 0:
+        nse = np.concatenate([nse, noise[:n - len(nse)]], axis=0)
+    return nse[:n] if len(noise) > n else nse
+
+
+def domixing(cleansamples, noisepossamples, noisenegsamples, snr_pos, snr_neg):
+    """SN/apply.py:56-104 (host arithmetic, float32 arrays with float64 scalars like the reference)."""
+    sig = np.asarray(cleansamples, np.float32)
+    nse_pos = _fit_noise(np.asarray(noisepossamples, np.float32), len(sig))
+    nse_neg = _fit_noise(np.asarray(noisenegsamples, np.float32), len(sig))
+    psignal = _seq_sum(abs(sig) * abs(sig)) / sig.shape[0]
+    pnoise_pos = _seq_sum(abs(nse_pos) * abs(nse_pos)) / nse_pos.shape[0]
+    pnoise_neg = _seq_sum(abs(nse_neg) * abs(nse_neg)) / nse_neg.shape[0]
+    K_pos = 1.0 if pnoise_pos == 0 else float(np.sqrt((psignal / pnoise_pos) * pow(10, -snr_pos / 10.0)))
+    K_neg = 1.0 if pnoise_neg == 0 else float(np.sqrt((psignal / pnoise_neg) * pow(10, -snr_neg / 10.0)))
+    noise_pos_scaled = np.float32(K_pos) * nse_pos
+    noise_neg_scaled = np.float32(K_neg) * nse_neg
+    mixed = sig + noise_pos_scaled + noise_neg_scaled
+    mixed = mixed / np.float32(float(max(abs(mixed))) + 0.000001)
+    d = np.float32(float(max(abs(mixed))) + 0.000001)          # the reference renormalises by the *normalised* mixture
+    target = (sig + noise_pos_scaled) / d
+    return mixed, target, K_pos, K_neg, noise_pos_scaled / d, noise_neg_scaled / d
+
+
+def _norm64(pcm):
+    x = np.asarray(pcm)
+    return (x / (float(max(abs(x))) + 0.000001)).astype(np.float32)
+
+
+def combine_signals(cleanpath, noisepospath, noisenegpath):
+    """SN/apply.py:107-139: normalise the three recordings, trim the speech to whole frames, mix at 0 dB / 0 dB.
+    -> (noise_pos_signal, noise_neg_signal, mixed, snr_pos, snr_neg)."""
+    clean = _norm64(read_wav(cleanpath))
+    pos = _norm64(read_wav(noisepospath))
+    neg = _norm64(read_wav(noisenegpath))
+    rem = (len(clean) - 400) % 160
+    if rem != 0:
+        clean = clean[:-rem]
+    snr_pos = snr_neg = 0                                         # SNRs[1]
+    mixed, _, _, _, pos_sig, neg_sig = domixing(clean, pos, neg, snr_pos, snr_neg)
+    return pos_sig, neg_sig, mixed, np.array(snr_pos, np.int32), np.array(snr_neg, np.int32)
+
+
+def apply_demo(speechpath, pospath, negpath, save_to):
+    """SN/apply.py:212-337: mix speech with a positive and a negative noise on the fly, condition on the first
+    200 frames of the scaled noises, process the mixture from frame 200 on.  Writes ``save_to`` and
+    ``save_to[:-15] + 'mixed_demo.wav'`` (float32, like the reference)."""
+    pos_sig, neg_sig, mixed, _, _ = combine_signals(speechpath, pospath, negpath)
+    eng = get_engine(VARIANT)
+    y, ymix = eng.enhance_demo(mixed, pos_sig, neg_sig, start=Noise_Win)
+    write_wav(save_to, y)
+    write_wav(save_to[:-15] + "mixed_demo.wav", ymix)
+    return y, ymix
+
+
 def recover_samples_from_spectrum(logspectrum_stft, spectrum_phase, save_to):
     """SN/apply.py:189-204: log-magnitude + phase -> samples (float32), written to ``save_to`` as float32 wav."""
     eng = get_engine(VARIANT)

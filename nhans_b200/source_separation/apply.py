@@ -16,7 +16,7 @@ import numpy as np
 from .. import weights as W
 from ..session import get_engine
 from ..wavio import FS, read_wav, write_wav
-from ..selective_noise.apply import _emit, _sibling
+from ..selective_noise.apply import _emit, _fit_noise, _norm64, _seq_sum, _sibling
 
 Noise_Win = 200
 Mix_Win = 35
@@ -42,6 +42,42 @@ def handle_signals(mixedpath, cleanpath, noisepath):
     clean = eng.normalise([read_wav(cleanpath)], trim=False)[0]
     noise = eng.normalise([read_wav(noisepath)], trim=False)[0]
     return clean, noise, mixed
+
+
+def domixing(cleansamples, noisesamples, snr):
+    """SS/apply.py:55-80 -> (mixed, K)."""
+    sig = np.asarray(cleansamples, np.float32)
+    nse = _fit_noise(np.asarray(noisesamples, np.float32), len(sig))
+    psignal = _seq_sum(abs(sig) * abs(sig)) / sig.shape[0]
+    pnoise = _seq_sum(abs(nse) * abs(nse)) / nse.shape[0]
+    K = float(np.sqrt(1.0 if pnoise == 0 else (psignal / pnoise) * pow(10, -snr / 10.0)))
+    mixed = sig + np.float32(K) * nse
+    return mixed / np.float32(float(max(abs(mixed))) + 0.000001), K
+
+
+def combine_signals(cleanpath, noisepath):
+    """SS/apply.py:83-108 -> (clean, noise * K, mixed, snr).  The reference slices ``clean[:-rem]`` even when
+    rem == 0 (which would empty the signal); a whole number of frames is kept as is here."""
+    clean = _norm64(read_wav(cleanpath))
+    noise = _norm64(read_wav(noisepath))
+    rem = (len(clean) - 400) % 160
+    if rem != 0:
+        clean = clean[:-rem]
+    snr = 0
+    mixed, K = domixing(clean, noise, snr)
+    return clean, noise * np.float32(K), mixed, np.array(snr, np.int32)
+
+
+def apply_demo(cleanpath, noisepath, save_to):
+    """SS/apply.py:179-285: on-the-fly 0 dB mixture of two speakers; contexts = first 200 frames of the clean
+    (target) and the scaled interfering speaker; frames [200:] are separated.  Writes ``save_to`` and
+    ``save_to[:-15] + 'mixed_demo.wav'``."""
+    clean, noise_k, mixed, _ = combine_signals(cleanpath, noisepath)
+    eng = get_engine(VARIANT)
+    y, ymix = eng.enhance_demo(mixed, noise_k, clean, start=Noise_Win)      # ctx_a = interference, ctx_b = target
+    write_wav(save_to, y)
+    write_wav(save_to[:-15] + "mixed_demo.wav", ymix)
+    return y, ymix
 
 
 def recover_samples_from_spectrum(logspectrum_stft, spectrum_phase, save_to):

@@ -321,3 +321,87 @@ def post_mix(denoised_samples, mixed_samples, compensate=0.0, ac=False):
     snr_est = float(np.mean(np.square(denoised_samples)) / np.mean(np.square(removed)))
     factor = snr_est / 20 if ac else compensate
     return removed, snr_est, denoised_samples + removed * factor
+
+
+# ---------------------------------------------------------------------------------------------
+# apply_demo (row n3): on-the-fly mixing + processing from frame 200 on
+# ---------------------------------------------------------------------------------------------
+def _pysum(x):
+    """Python builtin sum() over a float32 array as the reference calls it (SN/apply.py:77): sequential, and -
+    starting from int 0 under pre-NEP-50 numpy - carried in float64."""
+    acc = 0.0
+    for v in np.asarray(x, np.float64).tolist():
+        acc += v
+    return acc
+
+
+def _repeat_or_cut(noise, n):
+    """SN/apply.py:57-72."""
+    nse = noise
+    while n - len(nse) > 0:
+        diff = n - len(nse)
+        nse = np.concatenate([nse, noise[:diff]], axis=0)
+    if n - len(noise) < 0:
+        nse = noise[:n]
+    return nse
+
+
+def domixing_sn(clean, pos, neg, snr_pos=0, snr_neg=0):
+    """SN/apply.py:56-104 -> (mixed, noise_pos_signal, noise_neg_signal), float32."""
+    sig = clean
+    nse_pos, nse_neg = _repeat_or_cut(pos, len(sig)), _repeat_or_cut(neg, len(sig))
+    ps = _pysum(np.abs(sig) * np.abs(sig)) / sig.shape[0]
+    pp = _pysum(np.abs(nse_pos) * np.abs(nse_pos)) / nse_pos.shape[0]
+    pn = _pysum(np.abs(nse_neg) * np.abs(nse_neg)) / nse_neg.shape[0]
+    kp = 1.0 if pp == 0 else math.sqrt((ps / pp) * pow(10, -snr_pos / 10.0))
+    kn = 1.0 if pn == 0 else math.sqrt((ps / pn) * pow(10, -snr_neg / 10.0))
+    a = (np.float32(kp) * nse_pos).astype(np.float32)
+    b = (np.float32(kn) * nse_neg).astype(np.float32)
+    mixed = (sig + a + b).astype(np.float32)
+    mixed = (mixed / np.float32(float(np.max(np.abs(mixed))) + 0.000001)).astype(np.float32)
+    d = np.float32(float(np.max(np.abs(mixed))) + 0.000001)
+    return mixed, (a / d).astype(np.float32), (b / d).astype(np.float32)
+
+
+def domixing_ss(clean, noise, snr=0):
+    """SS/apply.py:55-80 -> (mixed, K)."""
+    nse = _repeat_or_cut(noise, len(clean))
+    ps = _pysum(np.abs(clean) * np.abs(clean)) / clean.shape[0]
+    pn = _pysum(np.abs(nse) * np.abs(nse)) / nse.shape[0]
+    k = math.sqrt(1.0 if pn == 0 else (ps / pn) * pow(10, -snr / 10.0))
+    mixed = (clean + np.float32(k) * nse).astype(np.float32)
+    return (mixed / np.float32(float(np.max(np.abs(mixed))) + 0.000001)).astype(np.float32), k
+
+
+def demo_signals(variant, clean_pcm, noise_a_pcm, noise_b_pcm=None):
+    """combine_signals (SN/apply.py:107-139, SS/apply.py:83-108) on in-memory PCM.
+    -> (mixed, ctx_a signal, ctx_b signal) in the engine's ctx order (SN: pos, neg; SS: interference, target)."""
+    clean = normalise(clean_pcm)
+    rem = (len(clean) - WIN) % HOP
+    if rem:
+        clean = clean[:-rem]
+    if variant == W.SELECTIVE_NOISE:
+        mixed, pos_sig, neg_sig = domixing_sn(clean, normalise(noise_a_pcm), normalise(noise_b_pcm))
+        return mixed, pos_sig, neg_sig
+    noise = normalise(noise_a_pcm)
+    mixed, k = domixing_ss(clean, noise)
+    return mixed, (noise * np.float32(k)).astype(np.float32), clean
+
+
+def apply_demo_arrays(net, mixed, sig_a, sig_b, mb=100):
+    """SN/apply.py:247-337 / SS/apply.py:198-285 after combine_signals -> (denoised samples, mixture-centre samples)."""
+    lm, ph = logmag_phase(mixed)
+    ca = context_of(logmag_phase(sig_a)[0])
+    cb = context_of(logmag_phase(sig_b)[0])
+    windows = strided_crop(lm[NOISE_WIN:], MIX_WIN, 1)
+    phs = ph[NOISE_WIN:]
+    dt = net.dtype
+    den = []
+    with torch.no_grad():
+        ea = net.tower(_t(ca, dt)[None])
+        eb = net.tower(_t(cb, dt)[None])
+        for i in range(int(math.ceil(windows.shape[0] / float(mb)))):
+            b = _t(windows[i * mb:(i + 1) * mb], dt)
+            den.append(net.mask_net(b, ea.expand(b.shape[0], -1), eb.expand(b.shape[0], -1)))
+    den = torch.cat(den, 0).to(torch.float32).numpy()
+    return istft(den, phs), istft(windows[:, MIX_WIN // 2, :], phs)
