@@ -62,6 +62,10 @@ int nhans_stft(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int U, f
 int nhans_stft_f32(nhans_ctx* ctx, const float* x, const int64_t* offs, int U, float* logmag, float* phase,
                    int64_t* frame_offs);
 
+/* Per-frame evaluation loss of the model graph (SN/main.py:243-246, SS/main.py:256-258):
+ * example_loss[i] = mean_k( (denoised[i][k] - target[i][k])^2 * linspace(2, 1, 201)[k] ), rows of 201 bins. */
+int nhans_eval_loss(nhans_ctx* ctx, const float* denoised, const float* target, int64_t n_frames, float* example_loss);
+
 /* Embedding tower (SN/main.py:189-202): ctx_logmag [R][200][201] -> emb [R][512]. */
 int nhans_embed(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb);
 

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(_HERE, "libnhans_b200.so")
 # every symbol include/nhans_b200.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "nhans_create", "nhans_destroy", "nhans_last_error", "nhans_load_weights", "nhans_normalise", "nhans_stft",
-    "nhans_stft_f32",
+    "nhans_stft_f32", "nhans_eval_loss",
     "nhans_embed", "nhans_masknet", "nhans_istft", "nhans_output_offsets", "nhans_enhance_batch", "nhans_sync",
     "nhans_upload", "nhans_run", "nhans_download", "nhans_postmix", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
     "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset",
@@ -53,6 +53,7 @@ def load():
     lib.nhans_normalise.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.nhans_stft.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.nhans_stft_f32.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.nhans_eval_loss.argtypes = [vp, vp, vp, i64, vp]
     lib.nhans_embed.argtypes = [vp, vp, i32, vp]
     lib.nhans_masknet.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.nhans_istft.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]

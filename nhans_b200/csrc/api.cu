@@ -642,6 +642,25 @@ int nhans_stft_f32(nhans_ctx* ctx, const float* x, const int64_t* offs, int U, f
   return NHANS_OK;
 }
 
+int nhans_eval_loss(nhans_ctx* ctx, const float* denoised, const float* target, int64_t n_frames, float* example_loss) {
+  if (!ctx || !denoised || !target || !example_loss || n_frames < 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  if (n_frames == 0) return NHANS_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)n_frames * kBins * 4;
+  CK(ctx->tmp[0].ensure(bytes));
+  CK(ctx->tmp[1].ensure(bytes));
+  CK(ctx->tmp[2].ensure((size_t)n_frames * 4));
+  CK(cudaMemcpyAsync(ctx->tmp[0].p, denoised, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tmp[1].p, target, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ProfScope ps(ctx, 4, 0, 0);
+    CK(launch_eval_loss(ctx->stream, ctx->tmp[0].as<float>(), ctx->tmp[1].as<float>(), n_frames, ctx->tmp[2].as<float>()));
+  }
+  CK(cudaMemcpyAsync(example_loss, ctx->tmp[2].p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NHANS_OK;
+}
+
 int nhans_embed(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb) {
   if (!ctx || !ctx_logmag || !emb || R <= 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
   CK(cudaSetDevice(ctx->device));

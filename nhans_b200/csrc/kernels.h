@@ -110,6 +110,7 @@ cudaError_t launch_normalise(cudaStream_t s, const int16_t* pcm, const long long
 // frames, window, FFT-400, log(|X| + 1e-5), angle: logmag/phase rows [frame_offs[u] + t][201]
 cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* offs, const long long* frame_offs, int U,
                         const int* peak, int max_frames_per_clip, long long total_frames, float* logmag, float* phase);
+cudaError_t launch_eval_loss(cudaStream_t s, const float* den, const float* tgt, long long n, float* loss);
 cudaError_t launch_stft_f32(cudaStream_t s, const float* x, const long long* offs, const long long* frame_offs, int U,
                             int max_frames_per_clip, float* logmag, float* phase);
 // exp(logmag) * e^{j phase} -> irfft-400 -> synthesis window -> overlap-add -> f32 / int16 samples

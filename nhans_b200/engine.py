@@ -159,6 +159,39 @@ class Engine:
         ymix, _ = self.istft(sl, sp, f1)
         return y, ymix
 
+    def eval_loss(self, denoised, target):
+        """example_loss of the model graph (SN/main.py:243-246): [n,201] x [n,201] -> [n]."""
+        d = np.ascontiguousarray(denoised, np.float32).reshape(-1, N_BINS)
+        t = np.ascontiguousarray(target, np.float32).reshape(-1, N_BINS)
+        assert d.shape == t.shape
+        out = np.zeros(d.shape[0], np.float32)
+        self._ck(self.lib.nhans_eval_loss(self.h, _ptr(d), _ptr(t), d.shape[0], _ptr(out)))
+        return out
+
+    def eval_outputs(self, mixed, target, sig_a, sig_b, extra=(), start=CTX_FRAMES):
+        """Eval-mode example stream + model outputs for one seed tuple (SN/reader.py:398-420 + SN/main.py:231-252):
+        STFT of the float signals, contexts = first 200 frames of sig_a / sig_b, frames [start:] of the mixture
+        through the mask network, per-frame loss against the target's log-magnitude.  ``extra`` signals are only
+        transformed (their log-magnitude / phase rows [start:] are returned, e.g. the SN pos / neg references)."""
+        sigs = [mixed, target, sig_a, sig_b] + list(extra)
+        lm, ph, fo = self.stft_f32(sigs)
+        T = int(fo[1])
+        for u in (2, 3):
+            if fo[u + 1] - fo[u] < CTX_FRAMES:
+                raise NhansError(-4, "context signal yields %d < 200 STFT frames" % (fo[u + 1] - fo[u]))
+        if T <= start or fo[2] - fo[1] != T:
+            raise NhansError(-2, "mixture / target frame counts %d / %d (need > %d and equal)" % (T, fo[2] - fo[1], start))
+        emb = self.embed(np.stack([lm[fo[2]:fo[2] + CTX_FRAMES], lm[fo[3]:fo[3] + CTX_FRAMES]]))
+        sl = np.ascontiguousarray(lm[start:T])
+        den = self.masknet(sl, np.array([0, T - start], np.int64), emb[0:1], emb[1:2])
+        tgt = np.ascontiguousarray(lm[fo[1] + start:fo[2]])
+        out = dict(loss=self.eval_loss(den, tgt), mixed=sl, denoised=den, mixedph=np.ascontiguousarray(ph[start:T]),
+                   target=tgt, targetph=np.ascontiguousarray(ph[fo[1] + start:fo[2]]),
+                   location=np.arange(T - start, dtype=np.int32))
+        out["extra"] = [(np.ascontiguousarray(lm[fo[4 + i] + start:fo[5 + i]]), np.ascontiguousarray(ph[fo[4 + i] + start:fo[5 + i]]))
+                        for i in range(len(extra))]
+        return out
+
     def embed(self, ctx_logmag):
         x = np.ascontiguousarray(ctx_logmag, np.float32).reshape(-1, CTX_FRAMES, N_BINS)
         emb = np.zeros((x.shape[0], 512), np.float32)

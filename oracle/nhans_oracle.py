@@ -346,8 +346,8 @@ def _repeat_or_cut(noise, n):
     return nse
 
 
-def domixing_sn(clean, pos, neg, snr_pos=0, snr_neg=0):
-    """SN/apply.py:56-104 -> (mixed, noise_pos_signal, noise_neg_signal), float32."""
+def domixing_sn(clean, pos, neg, snr_pos=0, snr_neg=0, with_target=False):
+    """SN/apply.py:56-104 == SN/reader.py:131-180 -> (mixed, noise_pos_signal, noise_neg_signal[, target]), float32."""
     sig = clean
     nse_pos, nse_neg = _repeat_or_cut(pos, len(sig)), _repeat_or_cut(neg, len(sig))
     ps = _pysum(np.abs(sig) * np.abs(sig)) / sig.shape[0]
@@ -360,6 +360,8 @@ def domixing_sn(clean, pos, neg, snr_pos=0, snr_neg=0):
     mixed = (sig + a + b).astype(np.float32)
     mixed = (mixed / np.float32(float(np.max(np.abs(mixed))) + 0.000001)).astype(np.float32)
     d = np.float32(float(np.max(np.abs(mixed))) + 0.000001)
+    if with_target:
+        return mixed, (a / d).astype(np.float32), (b / d).astype(np.float32), ((sig + a) / d).astype(np.float32)
     return mixed, (a / d).astype(np.float32), (b / d).astype(np.float32)
 
 
@@ -405,3 +407,65 @@ def apply_demo_arrays(net, mixed, sig_a, sig_b, mb=100):
             den.append(net.mask_net(b, ea.expand(b.shape[0], -1), eb.expand(b.shape[0], -1)))
     den = torch.cat(den, 0).to(torch.float32).numpy()
     return istft(den, phs), istft(windows[:, MIX_WIN // 2, :], phs)
+
+
+# ---------------------------------------------------------------------------------------------
+# eval-mode reader + model outputs (row n4)
+# ---------------------------------------------------------------------------------------------
+SNRS_SN = [-3, 0, 3, 5, 8]                 # SN/reader.py:205
+SNRS_SS = [-5, -3, -1, 0, 1, 3, 5]         # SS/reader.py:138
+
+
+def eval_snrs(variant, cleanpath):
+    """SN/reader.py:215-219 / SS/reader.py:147-148: SNRs picked by the MD5 of the clean path (bytes)."""
+    import hashlib
+    h = hashlib.md5(cleanpath if isinstance(cleanpath, bytes) else cleanpath.encode("utf-8")).hexdigest()
+    if variant == W.SELECTIVE_NOISE:
+        return SNRS_SN[int(h[:8], 16) % len(SNRS_SN)], SNRS_SN[int(h[:6], 16) % len(SNRS_SN)]
+    return (SNRS_SS[int(h[:8], 16) % len(SNRS_SS)],)
+
+
+def eval_outputs_arrays(net, variant, cleanpath, clean_pcm, noise_a_pcm, noise_b_pcm=None, mb=100):
+    """get_examples(istrain=False) (SN/reader.py:398-420, SS/reader.py:300-313) + model outputs and per-example
+    loss (SN/main.py:231-252, SS/main.py:253-264) for one seed tuple -> dict of arrays."""
+    clean = normalise(clean_pcm)
+    rem = (len(clean) - WIN) % HOP
+    if rem:
+        clean = clean[:-rem]
+    snrs = eval_snrs(variant, cleanpath)
+    out = {}
+    if variant == W.SELECTIVE_NOISE:
+        mixed, pos_sig, neg_sig, target = domixing_sn(clean, normalise(noise_a_pcm), normalise(noise_b_pcm), snrs[0], snrs[1], with_target=True)
+        sig_a, sig_b = pos_sig, neg_sig
+        plm, pph = logmag_phase(pos_sig)
+        nlm, nph = logmag_phase(neg_sig)
+        out.update(pos=plm[NOISE_WIN:], posph=pph[NOISE_WIN:], neg=nlm[NOISE_WIN:], negph=nph[NOISE_WIN:],
+                   snr_pos=snrs[0], snr_neg=snrs[1])
+    else:
+        noise = normalise(noise_a_pcm)
+        mixed, k = domixing_ss(clean, noise, snrs[0])
+        target = clean
+        sig_a, sig_b = (noise * np.float32(k)).astype(np.float32), clean      # noisecontext, cleancontext
+        out.update(snr=snrs[0])
+    lm, ph = logmag_phase(mixed)
+    tlm, tph = logmag_phase(target)
+    ca, cb = context_of(logmag_phase(sig_a)[0]), context_of(logmag_phase(sig_b)[0])
+    windows = strided_crop(lm[NOISE_WIN:], MIX_WIN, 1)
+    dt = net.dtype
+    den = []
+    with torch.no_grad():
+        ea, eb = net.tower(_t(ca, dt)[None]), net.tower(_t(cb, dt)[None])
+        for i in range(int(math.ceil(windows.shape[0] / float(mb)))):
+            b = _t(windows[i * mb:(i + 1) * mb], dt)
+            den.append(net.mask_net(b, ea.expand(b.shape[0], -1), eb.expand(b.shape[0], -1)))
+    den = torch.cat(den, 0).to(torch.float32).numpy()
+    tgt = tlm[NOISE_WIN:]
+    imp = np.linspace(2, 1, NBIN, dtype=np.float32).reshape(1, NBIN)
+    loss = np.mean(np.square(den - tgt) * imp, axis=1, dtype=np.float32)
+    out.update(loss=loss, mixed=lm[NOISE_WIN:], denoised=den, mixedph=ph[NOISE_WIN:],
+               location=np.arange(den.shape[0], dtype=np.int32))
+    if variant == W.SELECTIVE_NOISE:
+        out.update(target=tgt, targetph=tph[NOISE_WIN:])
+    else:
+        out.update(clean=tgt)
+    return out
