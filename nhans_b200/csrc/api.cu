@@ -817,7 +817,7 @@ int nhans_run(nhans_ctx* ctx) {
   CK(b.peak_a.ensure(sizeof(int) * U));
   CK(b.peak_b.ensure(sizeof(int) * U));
   CK(b.logmag.ensure(sbytes + 4));
-  CK(b.phase.ensure(sbytes + 4));
+  CK(b.phase.ensure(2 * sbytes + 8));          // unit phasors (float2 per bin) between the two transforms
   CK(b.den.ensure(sbytes + 4));
   CK(b.ctxlm_b.ensure(cbytes));
   CK(b.emb_b.ensure((size_t)U * 512 * 4));
@@ -832,9 +832,9 @@ int nhans_run(nhans_ctx* ctx) {
   CK(launch_peaks(ctx->stream, b.b.as<int16_t>(), b.d_b_offs.as<long long>(), U, b.peak_b.as<int>()));
   ctx->launches += 2;
   {
-    ProfScope ps(ctx, 1, 0, 2.0 * b.mix_offs[U] + 2.0 * sbytes);
+    ProfScope ps(ctx, 1, 0, 2.0 * b.mix_offs[U] + 3.0 * sbytes);
     CK(launch_stft(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), b.d_frame_offs.as<long long>(), U,
-                   b.peak_mix.as<int>(), b.max_frames, b.total_frames, b.logmag.as<float>(), b.phase.as<float>()));
+                   b.peak_mix.as<int>(), b.max_frames, b.total_frames, b.logmag.as<float>(), b.phase.as<float>(), true));
   }
   {
     ProfScope ps(ctx, 4, 0, 0);
@@ -870,10 +870,10 @@ int nhans_run(nhans_ctx* ctx) {
                         b.den.as<float>())))
     return rc;
   {
-    ProfScope ps(ctx, 2, 0, 2.0 * sbytes + 6.0 * b.total_out);
+    ProfScope ps(ctx, 2, 0, 3.0 * sbytes + 6.0 * b.total_out);
     CK(launch_istft(ctx->stream, b.den.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
                     b.d_out_offs.as<long long>(), U, b.peak_mix.as<int>(), 0, b.max_frames, b.out_f32.as<float>(),
-                    b.out_i16.as<int16_t>()));
+                    b.out_i16.as<int16_t>(), true));
   }
   b.done = true;
   return NHANS_OK;
@@ -886,9 +886,9 @@ int nhans_download(nhans_ctx* ctx, int16_t* out_i16, float* out_f32, float* mixp
   CK(cudaSetDevice(ctx->device));
   if (mixproc_f32) {
     // 'mixed_processed.wav' (SN/apply.py:457-458): iSTFT of the window centres, i.e. of the input spectrogram
-    ProfScope ps(ctx, 2, 0, 2.0 * b.total_frames * kBins * 4 + 4.0 * b.total_out);
+    ProfScope ps(ctx, 2, 0, 3.0 * b.total_frames * kBins * 4 + 4.0 * b.total_out);
     CK(launch_istft(ctx->stream, b.logmag.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
-                    b.d_out_offs.as<long long>(), b.U, b.peak_mix.as<int>(), 0, b.max_frames, b.mixproc.as<float>(), nullptr));
+                    b.d_out_offs.as<long long>(), b.U, b.peak_mix.as<int>(), 0, b.max_frames, b.mixproc.as<float>(), nullptr, true));
     CK(cudaMemcpyAsync(mixproc_f32, b.mixproc.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (out_i16) CK(cudaMemcpyAsync(out_i16, b.out_i16.p, b.total_out * 2, cudaMemcpyDeviceToHost, ctx->stream));
@@ -907,10 +907,10 @@ int nhans_postmix(nhans_ctx* ctx, float compensate, int ac, float* mixed_f32, fl
   CK(b.sums.ensure(sizeof(double) * 2 * b.U));
   CK(b.snr.ensure(sizeof(float) * b.U));
   {
-    ProfScope ps(ctx, 2, 0, 3.0 * b.total_frames * kBins * 4 + 12.0 * b.total_out);
+    ProfScope ps(ctx, 2, 0, 4.0 * b.total_frames * kBins * 4 + 12.0 * b.total_out);
     CK(launch_istft_post(ctx->stream, b.den.as<float>(), b.logmag.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
                          b.d_out_offs.as<long long>(), b.U, b.max_frames, nullptr, b.mixproc.as<float>(), b.removed.as<float>(),
-                         b.sums.as<double>()));
+                         b.sums.as<double>(), true));
   }
   {
     ProfScope ps(ctx, 4, 0, 0);

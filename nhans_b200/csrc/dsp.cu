@@ -29,18 +29,26 @@ constexpr int kThreads = 256;
 
 __device__ float2 g_tw200[200];         // e^{-2 pi i t / 200}
 __device__ float2 g_tw400[201];         // e^{-2 pi i k / 400}
-__device__ float g_hann[400];           // 0.5 - 0.5 cos(2 pi n / 400)
-__device__ float g_winv[400];           // hann[n] / sum_j hann^2[n mod 160 + 160 j]
-__constant__ float2 c_tw25[25];         // e^{-2 pi i t / 25}
+__device__ __align__(16) float g_hann[400];           // 0.5 - 0.5 cos(2 pi n / 400)
+__device__ __align__(16) float g_winv[400];           // hann[n] / sum_j hann^2[n mod 160 + 160 j]
 
 using namespace fft;
 
+__device__ float2 g_tw25[25];            // e^{-2 pi i t / 25} (thread-dependent index: not __constant__)
+
+// Complex DFT-200 of nf frames held in shared memory: a -> b -> a -> b (three passes, a sync after each).
 template <bool INV>
-__device__ void fft200_block(const float2* __restrict__ in, float2* __restrict__ tmp, float2* __restrict__ out, int nf,
-                             const float2* __restrict__ s_tw200) {
-  for (int t = threadIdx.x; t < nf * 25; t += blockDim.x) fft200_step_a<INV>(in, tmp, t / 25, t % 25, s_tw200);
+__device__ __forceinline__ void fft200_tail(float2* __restrict__ a, float2* __restrict__ b, int nf) {
+  // pass B1 / B2 after the caller's pass A left its result in `a`
+  for (int t = threadIdx.x; t < nf * 40; t += blockDim.x) {
+    const int f = t / 40, r = t - f * 40;
+    fft200_step_b1<INV>(a, b, f, r / 5, r % 5, g_tw25);
+  }
   __syncthreads();
-  for (int t = threadIdx.x; t < nf * 8; t += blockDim.x) fft200_step_b<INV>(tmp, out, t >> 3, t & 7, c_tw25);
+  for (int t = threadIdx.x; t < nf * 40; t += blockDim.x) {
+    const int f = t / 40, r = t - f * 40;
+    fft200_step_b2<INV>(b, a, f, r & 7, r >> 3);
+  }
   __syncthreads();
 }
 
@@ -63,16 +71,17 @@ __global__ void peak_kernel(const int16_t* __restrict__ pcm, const long long* __
   }
 }
 
-// grid: (ceil(max_frames / kFB), U)
+// grid: (ceil(max_frames / kFB), U).  PHASOR: the second output is the unit phasor X / |X| as float2 ((1, 0) where
+// X = 0) instead of the angle - what the fused path keeps between the two transforms (no atan2 here,
+// no sincos in the inverse).  Windowing is fused into the first butterfly pass (every sample is used once there).
+template <bool PHASOR>
 __global__ void __launch_bounds__(kThreads)
 stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const long long* __restrict__ offs,
             const long long* __restrict__ frame_offs, const int* __restrict__ peak, float* __restrict__ logmag,
             float* __restrict__ phase) {
-  __shared__ float s_x[(kFB - 1) * kHop + kWin];
+  __shared__ __align__(16) float s_x[(kFB - 1) * kHop + kWin];
   __shared__ float2 s_a[kFB * 200];
   __shared__ float2 s_b[kFB * 200];
-  __shared__ float2 s_tw200[200];
-  __shared__ float2 s_tw400[201];
   const int u = blockIdx.y;
   const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
   const int t0 = blockIdx.x * kFB;
@@ -86,27 +95,40 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
     const double denom = (double)peak[u] + 0.000001;
     for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)pcm[base + i] / denom);
   }
-  for (int i = threadIdx.x; i < 200; i += blockDim.x) s_tw200[i] = g_tw200[i];
-  for (int i = threadIdx.x; i < 201; i += blockDim.x) s_tw400[i] = g_tw400[i];
   __syncthreads();
-  // window and pack even/odd samples into a complex-200 sequence
-  for (int i = threadIdx.x; i < nf * 200; i += blockDim.x) {
-    const int f = i / 200, m = i - f * 200;
-    const float2 xx = *reinterpret_cast<const float2*>(&s_x[f * kHop + 2 * m]);
-    s_a[i] = make_float2(xx.x * g_hann[2 * m], xx.y * g_hann[2 * m + 1]);
+  // pass A on the windowed, even/odd-packed samples z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 25 m1 + m2
+  for (int t = threadIdx.x; t < nf * 25; t += blockDim.x) {
+    const int f = t / 25, m2 = t - f * 25;
+    float2 v[8];
+#pragma unroll
+    for (int m1 = 0; m1 < 8; ++m1) {
+      const int m = 25 * m1 + m2;
+      const float2 xx = *reinterpret_cast<const float2*>(&s_x[f * kHop + 2 * m]);
+      const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + m);
+      v[m1] = make_float2(xx.x * h.x, xx.y * h.y);
+    }
+    dft8<false>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) s_a[f * 200 + k1 * 25 + m2] = cmul(v[k1], __ldg(&g_tw200[m2 * k1]));
   }
   __syncthreads();
-  fft200_block<false>(s_a, s_b, s_a, nf, s_tw200);
+  fft200_tail<false>(s_a, s_b, nf);
   // X[k] = (Z[k] + conj Z[200-k]) / 2 - (i/2) e^{-2 pi i k / 400} (Z[k] - conj Z[200-k]),  k = 0..200
   const long long row0 = frame_offs[u] + t0;
   for (int i = threadIdx.x; i < nf * kBinsD; i += blockDim.x) {
     const int f = i / kBinsD, k = i - f * kBinsD;
-    const float2 X = rfft_post(s_a + f * 200, k, s_tw400);
+    const float2 X = rfft_post(s_a + f * 200, k, g_tw400);
     const float re = X.x, im = X.y;
-    const float mag = sqrtf(re * re + im * im);
     const size_t o = (size_t)(row0 + f) * kBinsD + k;
-    logmag[o] = logf(mag + 1e-5f);
-    if (phase) phase[o] = atan2f(im, re);
+    if (PHASOR) {
+      const float r2 = re * re + im * im;
+      const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
+      logmag[o] = __logf(r2 * inv + 1e-5f);
+      reinterpret_cast<float2*>(phase)[o] = r2 > 0.f ? make_float2(re * inv, im * inv) : make_float2(1.f, 0.f);
+    } else {
+      logmag[o] = __logf(sqrtf(re * re + im * im) + 1e-5f);
+      if (phase) phase[o] = atan2f(im, re);
+    }
   }
 }
 
@@ -124,19 +146,12 @@ __global__ void normalise_kernel(const int16_t* __restrict__ pcm, const long lon
 struct IstftSmem {
   float2 s[(kOH + 2) * kBinsD];           // spectrum, then FFT scratch, then the time-domain frames
   float2 a[(kOH + 2) * 200];
-  float2 tw200[200];
-  float2 tw400[201];
-  float winv[kWin];
 };
-
-__device__ __forceinline__ void istft_load_tables(IstftSmem& sm) {
-  for (int i = threadIdx.x; i < 200; i += blockDim.x) sm.tw200[i] = g_tw200[i];
-  for (int i = threadIdx.x; i < 201; i += blockDim.x) sm.tw400[i] = g_tw400[i];
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) sm.winv[i] = g_winv[i];
-}
 
 // exp(logmag) e^{j phase} -> irfft-400 -> synthesis window for frames fa .. fa + kOH + 1 of clip rows
 // [row0, row0 + T); leaves the windowed frames in sm.s viewed as float [kOH + 2][400].
+// PHASOR: `phase` holds unit phasors (float2) instead of angles.
+template <bool PHASOR>
 __device__ __forceinline__ float* istft_frames(IstftSmem& sm, const float* __restrict__ logmag,
                                                const float* __restrict__ phase, long long row0, int T, int fa) {
   constexpr int NF = kOH + 2;
@@ -148,28 +163,38 @@ __device__ __forceinline__ float* istft_frames(IstftSmem& sm, const float* __res
     if (t >= 0 && t < T) {
       const size_t o = (size_t)(row0 + t) * kBinsD + k;
       const float a = expf(logmag[o]);
-      float sn, cs;
-      sincosf(phase[o], &sn, &cs);
-      v = make_float2(a * cs, a * sn);
+      if (PHASOR) {
+        const float2 ph = reinterpret_cast<const float2*>(phase)[o];
+        v = make_float2(a * ph.x, a * ph.y);
+      } else {
+        float sn, cs;
+        sincosf(phase[o], &sn, &cs);
+        v = make_float2(a * cs, a * sn);
+      }
       if (k == 0 || k == 200) v.y = 0.f;  // irfft ignores the imaginary part of DC / Nyquist
     }
     sm.s[i] = v;
   }
   __syncthreads();
-  // Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]),  k = 0..199
-  for (int i = threadIdx.x; i < NF * 200; i += blockDim.x) {
-    const int f = i / 200, k = i - f * 200;
-    sm.a[i] = irfft_pre(sm.s + f * kBinsD, k, sm.tw400);
+  // Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]), fused into butterfly pass A
+  for (int t = threadIdx.x; t < NF * 25; t += blockDim.x) {
+    const int f = t / 25, m2 = t - f * 25;
+    float2 v[8];
+#pragma unroll
+    for (int m1 = 0; m1 < 8; ++m1) v[m1] = irfft_pre(sm.s + f * kBinsD, 25 * m1 + m2, g_tw400);
+    dft8<true>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) sm.a[f * 200 + k1 * 25 + m2] = cmul(v[k1], cconj(__ldg(&g_tw200[m2 * k1])));
   }
   __syncthreads();
-  fft200_block<true>(sm.a, sm.s, sm.a, NF, sm.tw200);
+  fft200_tail<true>(sm.a, sm.s, NF);
   // frames: y_f[2m] = Re z[m] / 400, y_f[2m+1] = Im z[m] / 400, times the synthesis window
   float* s_y = reinterpret_cast<float*>(sm.s);          // [NF][400]
   for (int i = threadIdx.x; i < NF * 200; i += blockDim.x) {
     const int f = i / 200, m = i - f * 200;
     const float2 z = sm.a[i];
-    s_y[f * kWin + 2 * m] = z.x * (1.0f / 400.0f) * sm.winv[2 * m];
-    s_y[f * kWin + 2 * m + 1] = z.y * (1.0f / 400.0f) * sm.winv[2 * m + 1];
+    const float2 w = __ldg(reinterpret_cast<const float2*>(g_winv) + m);
+    *reinterpret_cast<float2*>(&s_y[f * kWin + 2 * m]) = make_float2(z.x * (1.0f / 400.0f) * w.x, z.y * (1.0f / 400.0f) * w.y);
   }
   __syncthreads();
   return s_y;
@@ -185,6 +210,7 @@ __device__ __forceinline__ float ola_sample(const float* s_y, int i) {
 }
 
 // grid: (ceil((max_frames + 2) / kOH), U).  Output hop h (160 samples) sums frames h-2, h-1, h.
+template <bool PHASOR>
 __global__ void __launch_bounds__(kThreads)
 istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, const long long* __restrict__ frame_offs,
              const long long* __restrict__ out_offs, const int* __restrict__ peak, float* __restrict__ out_f32,
@@ -195,8 +221,7 @@ istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, 
   if (T <= 0) return;
   const int h0 = blockIdx.x * kOH;        // first output hop
   if (h0 >= T + 2) return;
-  istft_load_tables(sm);
-  const float* s_y = istft_frames(sm, logmag, phase, frame_offs[u], T, h0 - 2);
+  const float* s_y = istft_frames<PHASOR>(sm, logmag, phase, frame_offs[u], T, h0 - 2);
   const long long n_out = out_offs[u + 1] - out_offs[u];   // (T - 1) * 160 + 400
   const float scale = (float)((double)peak[u] + 0.000001);
   for (int i = threadIdx.x; i < kOH * kHop; i += blockDim.x) {
@@ -216,6 +241,7 @@ istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, 
 // Post-mix outputs of apply_snc (SN/apply.py:456-464) fused into one pass: both inverse STFTs (denoised
 // spectrum and the input spectrum = 'mixed_processed'), removed = mixed_processed - denoised, and the two
 // per-clip energy sums of snr_est = mean(denoised^2) / mean(removed^2).
+template <bool PHASOR>
 __global__ void __launch_bounds__(kThreads)
 istft_post_kernel(const float* __restrict__ den_logmag, const float* __restrict__ mix_logmag, const float* __restrict__ phase,
                   const long long* __restrict__ frame_offs, const long long* __restrict__ out_offs,
@@ -228,16 +254,15 @@ istft_post_kernel(const float* __restrict__ den_logmag, const float* __restrict_
   if (T <= 0) return;
   const int h0 = blockIdx.x * kOH;
   if (h0 >= T + 2) return;
-  istft_load_tables(sm);
   constexpr int PER = (kOH * kHop + kThreads - 1) / kThreads;
   float den[PER];
-  const float* s_y = istft_frames(sm, den_logmag, phase, frame_offs[u], T, h0 - 2);
+  const float* s_y = istft_frames<PHASOR>(sm, den_logmag, phase, frame_offs[u], T, h0 - 2);
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int i = threadIdx.x + k * kThreads;
     den[k] = i < kOH * kHop ? ola_sample(s_y, i) : 0.f;
   }
-  s_y = istft_frames(sm, mix_logmag, phase, frame_offs[u], T, h0 - 2);
+  s_y = istft_frames<PHASOR>(sm, mix_logmag, phase, frame_offs[u], T, h0 - 2);
   const long long n_out = out_offs[u + 1] - out_offs[u];
   float e_den = 0.f, e_rem = 0.f;
 #pragma unroll
@@ -326,7 +351,7 @@ cudaError_t dsp_init_tables() {
   cudaError_t e;
   if ((e = cudaMemcpyToSymbol(g_tw200, t200.data(), sizeof(float2) * 200)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_tw400, t400.data(), sizeof(float2) * 201)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyToSymbol(c_tw25, t25.data(), sizeof(float2) * 25)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(g_tw25, t25.data(), sizeof(float2) * 25)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_hann, hann.data(), sizeof(float) * 400)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_winv, winv.data(), sizeof(float) * 400)) != cudaSuccess) return e;
   return cudaSuccess;
@@ -339,11 +364,13 @@ cudaError_t launch_peaks(cudaStream_t s, const int16_t* pcm, const long long* of
 }
 
 cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* offs, const long long* frame_offs, int U,
-                        const int* peak, int max_frames_per_clip, long long total_frames, float* logmag, float* phase) {
+                        const int* peak, int max_frames_per_clip, long long total_frames, float* logmag, float* phase,
+                        bool phasor) {
   (void)total_frames;
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
-  stft_kernel<<<grid, kThreads, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
+  if (phasor) stft_kernel<true><<<grid, kThreads, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
+  else stft_kernel<false><<<grid, kThreads, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
   return cudaGetLastError();
 }
 
@@ -351,7 +378,7 @@ cudaError_t launch_stft_f32(cudaStream_t s, const float* x, const long long* off
                             int max_frames_per_clip, float* logmag, float* phase) {
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
-  stft_kernel<<<grid, kThreads, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
+  stft_kernel<false><<<grid, kThreads, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
   return cudaGetLastError();
 }
 
@@ -365,23 +392,26 @@ cudaError_t launch_normalise(cudaStream_t s, const int16_t* pcm, const long long
 
 cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase, const long long* frame_offs,
                          const long long* out_offs, int U, const int* peak, long long total_blocks_hint,
-                         int max_frames_per_clip, float* out_f32, int16_t* out_i16) {
+                         int max_frames_per_clip, float* out_f32, int16_t* out_i16, bool phasor) {
   (void)total_blocks_hint;
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + 2 + kOH - 1) / kOH, U);
-  istft_kernel<<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  if (phasor) istft_kernel<true><<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  else istft_kernel<false><<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
   return cudaGetLastError();
 }
 
 cudaError_t launch_istft_post(cudaStream_t s, const float* den_logmag, const float* mix_logmag, const float* phase,
                               const long long* frame_offs, const long long* out_offs, int U, int max_frames_per_clip,
-                              float* den_f32, float* mixed_f32, float* removed_f32, double* sums) {
+                              float* den_f32, float* mixed_f32, float* removed_f32, double* sums, bool phasor) {
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * U, s);
   if (e != cudaSuccess) return e;
   dim3 grid((max_frames_per_clip + 2 + kOH - 1) / kOH, U);
-  istft_post_kernel<<<grid, kThreads, 0, s>>>(den_logmag, mix_logmag, phase, frame_offs, out_offs, den_f32, mixed_f32,
-                                              removed_f32, sums);
+  if (phasor)
+    istft_post_kernel<true><<<grid, kThreads, 0, s>>>(den_logmag, mix_logmag, phase, frame_offs, out_offs, den_f32, mixed_f32, removed_f32, sums);
+  else
+    istft_post_kernel<false><<<grid, kThreads, 0, s>>>(den_logmag, mix_logmag, phase, frame_offs, out_offs, den_f32, mixed_f32, removed_f32, sums);
   return cudaGetLastError();
 }
 

@@ -86,6 +86,31 @@ NHANS_HD void fft200_step_b(const float2* tmp, float2* out, int f, int k1, const
   }
 }
 
+// The same DFT-25 as two radix-5 passes with 40 independent tasks per frame each (the kernels use these: one
+// task per thread keeps all lanes busy, the monolithic step B has only 8 tasks per frame).
+// pass B1 (one call per (f, k1, b)): g[b][c] = W25^{bc} sum_a y[5a + b] W5^{ac}
+template <bool INV>
+NHANS_HD void fft200_step_b1(const float2* tmp, float2* g, int f, int k1, int b, const float2* tw25) {
+  const float2* y = tmp + f * 200 + k1 * 25;
+  float2 o0, o1, o2, o3, o4;
+  dft5<INV>(y[b], y[5 + b], y[10 + b], y[15 + b], y[20 + b], o0, o1, o2, o3, o4);
+  float2* gg = g + f * 200 + k1 * 25 + b * 5;
+  gg[0] = o0;
+  gg[1] = cmul(o1, tw<INV>(tw25[b]));
+  gg[2] = cmul(o2, tw<INV>(tw25[2 * b]));
+  gg[3] = cmul(o3, tw<INV>(tw25[3 * b]));
+  gg[4] = cmul(o4, tw<INV>(tw25[4 * b]));
+}
+// pass B2 (one call per (f, k1, c)): Z[k1 + 8 (c + 5 d)] = sum_b g[b][c] W5^{bd}
+template <bool INV>
+NHANS_HD void fft200_step_b2(const float2* g, float2* out, int f, int k1, int c) {
+  const float2* gg = g + f * 200 + k1 * 25 + c;
+  float2 z0, z1, z2, z3, z4;
+  dft5<INV>(gg[0], gg[5], gg[10], gg[15], gg[20], z0, z1, z2, z3, z4);
+  float2* o = out + f * 200 + k1;
+  o[8 * c] = z0; o[8 * (c + 5)] = z1; o[8 * (c + 10)] = z2; o[8 * (c + 15)] = z3; o[8 * (c + 20)] = z4;
+}
+
 // rfft-400 bin k (0..200) from the DFT-200 Z of the packed sequence z[m] = x[2m] + i x[2m+1]:
 // X[k] = (Z[k] + conj Z[200-k]) / 2 - (i/2) e^{-2 pi i k / 400} (Z[k] - conj Z[200-k])
 NHANS_HD float2 rfft_post(const float2* Z, int k, const float2* tw400) {

@@ -24,6 +24,16 @@ int main() {
     for (int m = 0; m < 200; ++m) a[f * 200 + m] = make_float2(x[f * 400 + 2 * m], x[f * 400 + 2 * m + 1]);
   for (int f = 0; f < NF; ++f) for (int m2 = 0; m2 < 25; ++m2) fft200_step_a<false>(a.data(), b.data(), f, m2, t200.data());
   for (int f = 0; f < NF; ++f) for (int k1 = 0; k1 < 8; ++k1) fft200_step_b<false>(b.data(), c.data(), f, k1, t25.data());
+  {  // the split radix-5 passes give the same DFT-25 as the monolithic step B
+    std::vector<float2> g(NF * 200), c2(NF * 200);
+    for (int f = 0; f < NF; ++f) for (int k1 = 0; k1 < 8; ++k1) for (int bb = 0; bb < 5; ++bb) fft200_step_b1<false>(b.data(), g.data(), f, k1, bb, t25.data());
+    for (int f = 0; f < NF; ++f) for (int k1 = 0; k1 < 8; ++k1) for (int cc = 0; cc < 5; ++cc) fft200_step_b2<false>(g.data(), c2.data(), f, k1, cc);
+    double d = 0;
+    for (int i = 0; i < NF * 200; ++i) d = fmax(d, fmax(fabs(c2[i].x - c[i].x), fabs(c2[i].y - c[i].y)));
+    printf("split step B max diff %.3e\n", d);
+    if (d > 1e-4) return 2;
+    c = c2;
+  }
   double max_err = 0, max_mag = 0;
   std::vector<float2> S(NF * 201);
   for (int f = 0; f < NF; ++f)
