@@ -24,7 +24,7 @@ constexpr int kWin = 400;
 constexpr int kHop = 160;
 constexpr int kBinsD = 201;
 constexpr int kFB = 10;                 // frames per CTA (forward)
-constexpr int kOH = 8;                  // output hops per CTA (inverse) -> kOH + 2 frames
+constexpr int kOH = 12;                 // output hops per CTA (inverse) -> kOH + 2 frames (2 / 12 recomputed)
 constexpr int kThreads = 256;
 
 __device__ float2 g_tw200[200];         // e^{-2 pi i t / 200}
@@ -92,8 +92,10 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
   if (xf) {                              // already-normalised float samples (apply_demo, SN/apply.py:241-247)
     for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = xf[base + i];
   } else {
-    const double denom = (double)peak[u] + 0.000001;
-    for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)pcm[base + i] / denom);
+    // x / (peak + 1e-6) in float64 like the reference, as a multiplication by the float64 reciprocal (differs from
+    // the true quotient by < 1 float64 ulp before the rounding to float32; nhans_normalise keeps the exact division)
+    const double inv = 1.0 / ((double)peak[u] + 0.000001);
+    for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)pcm[base + i] * inv);
   }
   __syncthreads();
   // pass A on the windowed, even/odd-packed samples z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 25 m1 + m2

@@ -24,6 +24,7 @@
 // The epilogue is the fusion of blocks.py:104-108 (batch-norm), main.py:166,172 (conditioning adds),
 // main.py:184-186 (residual add, ReLU) folded as in SURVEY.md App. A.6.
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -150,6 +151,7 @@ constexpr int kEpiR1 = 4;         // + r1_vec[c] * raw spectrogram value (1x1 tr
 constexpr int kEpiTabS = 8;       // time / frequency embedding tables (fp16) resident in shared memory
 constexpr int kEpiTabG = 16;      // combined fp32 embedding table read from global memory
 constexpr int kEpiHead = 32;      // last_dense: fp32 out + centre frame
+constexpr int kEpiRow = 64;       // row-per-thread epilogue (below) instead of the transposing one
 
 // One epilogue warp.  ew = 0..7: TMEM lane quarter q = ew & 3, and the two warps of a quarter (half = ew >> 2)
 // take alternate 16-column chunks.  Per chunk: tcgen05.ld (thread = row) -> XOR-swizzled 32 x 16 fp32 transpose
@@ -362,6 +364,205 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
   if (p.debug_stats && ew == 0 && lane == 0) atomicAdd(p.debug_stats + 3, (unsigned long long)w_full);
 }
 
+__device__ __forceinline__ void ldg256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// Row-per-thread epilogue.  The transposing epilogue above keeps global accesses coalesced at the price of two
+// shared-memory passes per accumulator element; in the 64/128-channel layers those passes compete with the
+// tensor core's own operand reads for the shared-memory pipe (ncu: 34 % LSU + 42 % tensor wavefronts, tensor pipe
+// 57 % active).  Here a thread keeps the row tcgen05.ld hands it (thread = TMEM lane = GEMM row) and works on 16
+// consecutive channels: one 32-byte residual load and one 32-byte store per chunk (256-bit accesses, a full
+// sector each), per-channel vectors and the fp16 time / frequency tables from shared memory (frequency rows
+// padded by 16 bytes so that the 32 rows of a warp hit different banks), no staging, no metadata exchange.
+template <int EPI, bool CTA2>
+__device__ __forceinline__ void epilogue_warp_row(Ctrl* ctrl, const GemmDev& p, const GemmCfg& cfg, int ew, int lane,
+                                                  uint32_t tmem_base, int num_tiles, int n_tiles, const __half* s_ttab,
+                                                  const __half* s_ftab, const float* s_rs, const float* s_r1, uint32_t rank) {
+  constexpr bool kPair = EPI & kEpiPair, kRes = EPI & kEpiRes, kR1 = EPI & kEpiR1, kTabS = EPI & kEpiTabS,
+                 kTabG = EPI & kEpiTabG;
+  const EpiDev& e = p.epi;
+  const int MT = cfg.mt;
+  const int q = ew & 3, half = ew >> 2;
+  const int hw = p.Hq * p.Wq;
+  const int NV = kPair ? 2 * MT : MT;
+  const int vcols = kPair ? e.n_real : p.BN;
+  const int tab_C = kPair ? e.n_real : p.N;
+  const int tab_W = kPair ? e.pair_W : p.Wo;
+  const int f_pitch = tab_C + 8;
+  const int half_W = (tab_W + 1) >> 1;
+  struct LoadSet {
+    float4 b[4], t[4];
+    uint4 x[2];
+  };
+  const int cta_shift = CTA2 ? 1 : 0;
+  const int sub_rows = 128 << cta_shift;
+  uint32_t it = 0;
+  long long w_full = 0;
+  auto release_acc = [&](uint32_t acc) {
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CTA2) ptx::mbar_arrive_cluster(&ctrl->tmem_empty[acc], 0);
+      else ptx::mbar_arrive(&ctrl->tmem_empty[acc]);
+    }
+  };
+  for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
+    const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+    const int n0 = (tile % n_tiles) * p.BN;
+    if (p.debug_skip_epilogue == 1) {
+      ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
+      release_acc(acc);
+      continue;
+    }
+    const int tile_m0 = (tile / n_tiles) * (MT * sub_rows) + (int)rank * 128;
+    bool waited = false;
+    bool row_ok = false;
+    int unit = 0, ho = 0, wb = 0, utt = 0;
+#pragma unroll 1
+    for (int v = 0; v < NV; ++v) {
+      const int i = kPair ? (v >> 1) : v, j = kPair ? (v & 1) : 0;
+      const int m0 = tile_m0 + i * sub_rows;
+      if (m0 >= p.M) break;
+      const int m = m0 + q * 32 + lane;
+      if (!kPair || j == 0) {                 // the row this thread owns in sub-tile i
+        row_ok = m < p.M;
+        unit = m / hw;
+        const int rem = m - unit * hw;
+        ho = rem / p.Wq;
+        wb = rem - ho * p.Wq;
+        row_ok = row_ok && ho < p.Ho && wb < p.Wo;
+        utt = row_ok ? p.units.utt[unit] : 0;
+      }
+      const int wo = kPair ? 2 * wb + j : wb;
+      const bool ok = row_ok && (!kPair || wo < e.pair_W);
+      float rawv = 0.f;
+      size_t o_out = 0, o_bias = 0, o_res = 0, o_tf = 0;
+      int o_t = 0, o_f = 0;
+      if (ok) {
+        if (kR1) {
+          const int frame = p.units.frame[unit] + ho * e.r1_sh + e.raw_oh;
+          if (frame >= p.units.lo[unit] && frame < p.units.hi[unit]) rawv = __ldg(e.raw + (size_t)frame * 201 + wo * e.r1_sw);
+        }
+        long long pix;
+        if (e.o_mode == 1) {
+          pix = ((long long)unit * e.o_W + wo) * e.o_H + ho;
+        } else {
+          const int y = ho + e.o_oy, x = wo + e.o_ox;
+          const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
+          pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw);
+        }
+        o_out = (size_t)pix * e.out_C + n0;
+        o_bias = (size_t)utt * e.bias_stride + n0;
+        if (kRes) o_res = (size_t)((long long)m + (kPair ? (j ? e.res_off1 : e.res_off0) : 0)) * e.res_C + n0;
+        if (kTabS) {
+          o_t = ho * tab_C + n0;
+          o_f = (kPair ? ((wo & 1) * half_W + (wo >> 1)) : wo) * f_pitch + n0;    // pair tables are stored by column parity
+        }
+        if (kTabG) o_tf = (size_t)(ho * tab_W + wo) * tab_C + n0;
+      }
+      auto issue_loads = [&](LoadSet& L, int c0) {
+        if (c0 >= vcols || !ok || p.debug_skip_epilogue == 2) return;
+        const float4* bp = reinterpret_cast<const float4*>(e.bias + o_bias + c0);
+        L.b[0] = __ldg(bp); L.b[1] = __ldg(bp + 1); L.b[2] = __ldg(bp + 2); L.b[3] = __ldg(bp + 3);
+        if (kTabG) {
+          const float4* tp = reinterpret_cast<const float4*>(e.tftab + o_tf + c0);
+          L.t[0] = __ldg(tp); L.t[1] = __ldg(tp + 1); L.t[2] = __ldg(tp + 2); L.t[3] = __ldg(tp + 3);
+        }
+        if (kRes) ldg256(e.res + o_res + c0, L.x[0], L.x[1]);
+      };
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + i * p.BN + (kPair ? j * e.n_real : 0);
+      auto process = [&](const LoadSet& L, int c0) {
+        uint32_t tv[16];
+        ptx::tmem_ld16(t_addr + c0, tv);
+        ptx::tmem_ld_wait();
+        if (!ok) return;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(tv[k]);
+        if (p.debug_skip_epilogue != 2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { f[4 * k] += L.b[k].x; f[4 * k + 1] += L.b[k].y; f[4 * k + 2] += L.b[k].z; f[4 * k + 3] += L.b[k].w; }
+          if (kTabG) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { f[4 * k] += L.t[k].x; f[4 * k + 1] += L.t[k].y; f[4 * k + 2] += L.t[k].z; f[4 * k + 3] += L.t[k].w; }
+          }
+        }
+        if (kTabS) {
+          uint4 tt[2], ff[2];
+          tt[0] = *reinterpret_cast<const uint4*>(s_ttab + o_t + c0);
+          tt[1] = *reinterpret_cast<const uint4*>(s_ttab + o_t + c0 + 8);
+          ff[0] = *reinterpret_cast<const uint4*>(s_ftab + o_f + c0);
+          ff[1] = *reinterpret_cast<const uint4*>(s_ftab + o_f + c0 + 8);
+          const __half2* th = reinterpret_cast<const __half2*>(tt);
+          const __half2* fh = reinterpret_cast<const __half2*>(ff);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 s2 = __half22float2(__hadd2(th[k], fh[k]));
+            f[2 * k] += s2.x;
+            f[2 * k + 1] += s2.y;
+          }
+        }
+        if (kRes && p.debug_skip_epilogue != 2) {
+          const __half2* xh = reinterpret_cast<const __half2*>(L.x);
+          const float4* rs = reinterpret_cast<const float4*>(s_rs + n0 + c0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 r = rs[k];
+            const float2 x0 = __half22float2(xh[2 * k]), x1 = __half22float2(xh[2 * k + 1]);
+            f[4 * k] = fmaf(r.x, x0.x, f[4 * k]); f[4 * k + 1] = fmaf(r.y, x0.y, f[4 * k + 1]);
+            f[4 * k + 2] = fmaf(r.z, x1.x, f[4 * k + 2]); f[4 * k + 3] = fmaf(r.w, x1.y, f[4 * k + 3]);
+          }
+        }
+        if (kR1) {
+          const float4* r1 = reinterpret_cast<const float4*>(s_r1 + n0 + c0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 r = r1[k];
+            f[4 * k] = fmaf(r.x, rawv, f[4 * k]); f[4 * k + 1] = fmaf(r.y, rawv, f[4 * k + 1]);
+            f[4 * k + 2] = fmaf(r.z, rawv, f[4 * k + 2]); f[4 * k + 3] = fmaf(r.w, rawv, f[4 * k + 3]);
+          }
+        }
+        if (e.relu) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+        }
+        uint4 o0, o1;
+        o0.x = pack_half2(f[0], f[1]); o0.y = pack_half2(f[2], f[3]); o0.z = pack_half2(f[4], f[5]); o0.w = pack_half2(f[6], f[7]);
+        o1.x = pack_half2(f[8], f[9]); o1.y = pack_half2(f[10], f[11]); o1.z = pack_half2(f[12], f[13]); o1.w = pack_half2(f[14], f[15]);
+        if (p.debug_skip_epilogue != 3) stg256(e.out + o_out + c0, o0, o1);
+      };
+      LoadSet A, B;
+      int c0 = ((half + v) & 1) * 16;
+      issue_loads(A, c0);
+      if (!waited) {
+        ptx::mbar_wait_timed(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4, &w_full);
+        ptx::tc_fence_after();
+        waited = true;
+      }
+#pragma unroll 1
+      for (; c0 < vcols; c0 += 64) {
+        issue_loads(B, c0 + 32);
+        process(A, c0);
+        if (c0 + 32 < vcols) {
+          issue_loads(A, c0 + 64);
+          process(B, c0 + 32);
+        }
+      }
+    }
+    if (!waited) ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
+    release_acc(acc);
+  }
+  if (p.debug_stats && ew == 0 && lane == 0) atomicAdd(p.debug_stats + 3, (unsigned long long)w_full);
+}
+
 template <int EPI, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -387,10 +588,36 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   for (int i = threadIdx.x; i < num_groups; i += blockDim.x) ctrl->groups[i] = p.groups[i];
   // optional shared-memory copies of the fp16 time / frequency embedding tables (after the epilogue staging)
-  __half* s_ttab = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + kEpiBytes);
+  constexpr bool kRow = (EPI & kEpiRow) != 0;
+  uint8_t* tab_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + (kRow ? 0 : kEpiBytes);
+  __half* s_ttab = reinterpret_cast<__half*>(tab_base);
   const int tab_C = p.epi.pair ? p.epi.n_real : p.N;
   __half* s_ftab = s_ttab + p.epi.tab_H * tab_C;
-  if (cfg.tab_bytes) {
+  float* s_rs = nullptr;
+  float* s_r1 = nullptr;
+  if (kRow) {
+    // row flavour: frequency rows padded by 8 halfs (pair layers: rows ordered by column parity, so that the rows of
+    // consecutive GEMM rows are consecutive), then the per-channel residual scale / rank-1 vectors as fp32
+    const bool tabs = (EPI & kEpiTabS) != 0;
+    const int f_pitch = tab_C + 8;
+    const int half_W = (p.epi.tab_W + 1) >> 1;
+    if (!tabs) s_ftab = s_ttab;
+    float* vec = reinterpret_cast<float*>(tabs ? reinterpret_cast<uint8_t*>(s_ftab) + (((size_t)p.epi.tab_W * f_pitch * 2 + 15) & ~(size_t)15)
+                                               : tab_base);
+    s_rs = vec;
+    s_r1 = vec + p.N;
+    if (tabs) {
+      const int nt = p.epi.tab_H * tab_C / 8, c8 = tab_C / 8;
+      for (int i = threadIdx.x; i < nt; i += blockDim.x) reinterpret_cast<uint4*>(s_ttab)[i] = reinterpret_cast<const uint4*>(p.epi.ttab16)[i];
+      for (int i = threadIdx.x; i < p.epi.tab_W * c8; i += blockDim.x) {
+        const int w = i / c8, c = i - w * c8;
+        const int r = p.epi.pair ? ((w & 1) * half_W + (w >> 1)) : w;
+        *reinterpret_cast<uint4*>(s_ftab + (size_t)r * f_pitch + c * 8) = reinterpret_cast<const uint4*>(p.epi.ftab16)[i];
+      }
+    }
+    if (EPI & kEpiRes) for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_rs[i] = p.epi.res_scale[i];
+    if (EPI & kEpiR1) for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_r1[i] = p.epi.r1_vec[i];
+  } else if (cfg.tab_bytes) {
     const int nt = p.epi.tab_H * tab_C / 8, nf = p.epi.tab_W * tab_C / 8;       // 16-byte units
     for (int i = threadIdx.x; i < nt; i += blockDim.x) reinterpret_cast<uint4*>(s_ttab)[i] = reinterpret_cast<const uint4*>(p.epi.ttab16)[i];
     for (int i = threadIdx.x; i < nf; i += blockDim.x) reinterpret_cast<uint4*>(s_ftab)[i] = reinterpret_cast<const uint4*>(p.epi.ftab16)[i];
@@ -490,7 +717,8 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     else mma_issuer<1, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
   } else {
     // ===================== epilogue (warps 0..7) =====================
-    epilogue_warp<EPI, CTA2>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab, rank);
+    if (kRow) epilogue_warp_row<EPI, CTA2>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab, s_rs, s_r1, rank);
+    else epilogue_warp<EPI, CTA2>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab, rank);
   }
 
   ptx::tc_fence_before();
@@ -505,22 +733,25 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
 }  // namespace
 
-int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, GemmCfg* cfg) {
+int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, int row, GemmCfg* cfg) {
   const int b_bytes = (cta2 ? BN / 2 : BN) * 128;
   GemmCfg c;
   c.cta2 = cta2;
-  // shared-memory tables only where the epilogue is the critical path (short main loops: BN <= 128)
-  c.tab_bytes = (BN <= 128 && tab_bytes > 0) ? ((tab_bytes + 127) & ~127) : 0;
+  c.row = row;
+  // shared-memory tables only where the epilogue is the critical path (short main loops: BN <= 128); the row
+  // flavour's tab_bytes (padded tables + per-channel vectors) is computed by the caller and always taken
+  c.tab_bytes = ((BN <= 128 || row) && tab_bytes > 0) ? ((tab_bytes + 127) & ~127) : 0;
   c.mt = 256 / BN < 1 ? 1 : 256 / BN;
   c.na = 4;
-  const int budget = kSmemLimit - 1024 - kCtrlBytes - kEpiBytes - c.tab_bytes - c.na * kSlabBytes;
+  const int epi_bytes = row ? 0 : kEpiBytes;
+  const int budget = kSmemLimit - 1024 - kCtrlBytes - epi_bytes - c.tab_bytes - c.na * kSlabBytes;
   c.nb = budget / b_bytes;
   if (c.nb > kMaxB) c.nb = kMaxB;
   c.resident = (num_kb <= c.nb && !cta2) ? 1 : 0;
   c.desc_mode = 0;
   c.il = c.mt >= 2 ? 2 : 1;
   if (cfg) *cfg = c;
-  return 1024 + c.na * kSlabBytes + c.nb * b_bytes + kCtrlBytes + kEpiBytes + c.tab_bytes;
+  return 1024 + c.na * kSlabBytes + c.nb * b_bytes + kCtrlBytes + epi_bytes + c.tab_bytes;
 }
 
 namespace {
@@ -566,10 +797,16 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   if (p.M <= 0) return cudaSuccess;
   if (p.num_groups > kMaxGroups || p.BN % 16 != 0 || p.BN > 256 || p.N % p.BN != 0) return cudaErrorInvalidValue;
   GemmCfg cfg;
-  const int tab_bytes = (p.epi.ttab16 && p.epi.ftab16) ? (p.epi.tab_H + p.epi.tab_W) * (p.epi.pair ? p.epi.n_real : p.N) * 2 : 0;
+  static const int row_env = getenv("NHANS_EPI_ROW") ? atoi(getenv("NHANS_EPI_ROW")) : 1;
+  // bit 0: row-per-thread epilogue for the 64/128-channel layers (BN <= 128), bit 1: for the BN = 256 layers too
+  const int row = (!p.epi.head && ((p.BN <= 128 && (row_env & 1)) || (p.BN > 128 && (row_env & 2)))) ? 1 : 0;
+  const int tab_C = p.epi.pair ? p.epi.n_real : p.N;
+  const bool tabs_fit = p.epi.ttab16 && p.epi.ftab16 && p.BN <= 128;
+  int tab_bytes = (p.epi.ttab16 && p.epi.ftab16) ? (p.epi.tab_H + p.epi.tab_W) * tab_C * 2 : 0;
+  if (row) tab_bytes = (tabs_fit ? p.epi.tab_H * tab_C * 2 + ((p.epi.tab_W * (tab_C + 8) * 2 + 15) & ~15) : 0) + 2 * p.N * 4;
   // CTA pairs whenever there is enough work for every pair and B splits into two legal boxes (debug: bit 4 of desc_mode disables)
   const int cta2 = (!(desc_mode & 16) && (p.BN % 32) == 0 && !p.epi.head && p.M >= 256 * (n_sm / 2)) ? 1 : 0;
-  const int smem = gemm_smem_bytes(p.BN, p.num_kb, tab_bytes, cta2, &cfg);
+  const int smem = gemm_smem_bytes(p.BN, p.num_kb, tab_bytes, cta2, row, &cfg);
   const CUtensorMap& mapB = cta2 ? mapB_half : mapB_full;
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
@@ -586,7 +823,8 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
     if (e.pair) fl |= kEpiPair;
     if (e.res) fl |= kEpiRes;
     if (e.r1_vec) fl |= kEpiR1;
-    if (e.tftab) fl |= cfg.tab_bytes ? kEpiTabS : kEpiTabG;
+    if (e.tftab) fl |= (row ? tabs_fit : cfg.tab_bytes != 0) ? kEpiTabS : kEpiTabG;
+    if (row) fl |= kEpiRow;
   }
 #define NHANS_FLAVOUR(F) \
   case F:                \
@@ -604,6 +842,17 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
     NHANS_FLAVOUR(kEpiPair | kEpiTabS)                 // pixel-pair rows (64-channel stage)
     NHANS_FLAVOUR(kEpiPair | kEpiTabS | kEpiRes)
     NHANS_FLAVOUR(kEpiPair | kEpiTabS | kEpiR1)
+    NHANS_FLAVOUR(kEpiRow)
+    NHANS_FLAVOUR(kEpiRow | kEpiR1)
+    NHANS_FLAVOUR(kEpiRow | kEpiTabS)
+    NHANS_FLAVOUR(kEpiRow | kEpiTabS | kEpiRes)
+    NHANS_FLAVOUR(kEpiRow | kEpiTabS | kEpiR1)
+    NHANS_FLAVOUR(kEpiRow | kEpiTabG)
+    NHANS_FLAVOUR(kEpiRow | kEpiTabG | kEpiRes)
+    NHANS_FLAVOUR(kEpiRow | kEpiTabG | kEpiR1)
+    NHANS_FLAVOUR(kEpiRow | kEpiPair | kEpiTabS)
+    NHANS_FLAVOUR(kEpiRow | kEpiPair | kEpiTabS | kEpiRes)
+    NHANS_FLAVOUR(kEpiRow | kEpiPair | kEpiTabS | kEpiR1)
     default: return cudaErrorInvalidValue;
   }
 #undef NHANS_FLAVOUR

@@ -58,6 +58,7 @@ struct GemmCfg {              // chosen by the host per layer shape
   int il;                     // sub-tiles whose MMAs are interleaved (1, 2 or 4; divides mt, <= na)
   int tab_bytes;              // > 0: the fp16 time / frequency tables are staged in shared memory
   int cta2;                   // 1: CTA pairs (cta_group::2): M = 256 MMAs, each CTA loads half of B
+  int row;                    // 1: row-per-thread epilogue (no shared-memory transpose), see gemm_tc.cu
 };
 
 struct GemmDev {
@@ -85,7 +86,7 @@ struct DirectDev {
 };
 
 constexpr int kGemmThreads = 352;     // A producer, B producer, MMA issuer, 8 epilogue warps
-int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, GemmCfg* cfg);
+int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, int row, GemmCfg* cfg);
 cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
                         const CUtensorMap& mapB, const CUtensorMap& mapBhalf, const GemmDev& p, int desc_mode);
