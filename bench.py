@@ -143,7 +143,18 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()                    # creates the communicator (the only NCCL use: barrier + max over ranks)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     eng = Engine(local_rank, variant, win_capacity=a.win_capacity)
     eng.load_weights(weights, wsrc)
 
@@ -225,9 +236,10 @@ def main():
         line = dict(base)
         line.update({
             "value": value, "ms_per_step": ms_res / a.steps, "dtype": "f16 operands, f32 accumulate",
-            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(mix.nbytes + neg.nbytes),
-                    "d2h_bytes_per_step": int(p_out.array.nbytes)},
-            "gpu_launches": int(st[5]["launches"]),
+            # whole-job figures: every rank copies its own shard and launches its own kernels
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": int(mix.nbytes + neg.nbytes) * world,
+                    "d2h_bytes_per_step": int(p_out.array.nbytes) * world},
+            "gpu_launches": int(st[5]["launches"]) * world,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_shift_kernel (tcgen05 implicit-GEMM conv layers)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
@@ -246,7 +258,7 @@ def main():
             "tensor_ceiling_audio_s_per_s": tf_peak * 1e3 / (GFLOP_PER_WINDOW * 100) * world,
         })
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(weights, variant, 2.0)
+            line["cpu_baseline"] = cpu_baseline(weights, variant, 4.0)    # BASELINE configs[0] in full: one 4 s utterance
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
