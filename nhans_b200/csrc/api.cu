@@ -289,8 +289,8 @@ void fill_out(EpiDev& e, const NetDev& net, const Grid& g) {
   e.out = g.buf >= 0 ? net.bufs[g.buf] : nullptr;
   e.out_C = g.C;
   e.o_mode = g.mode; e.o_sh = g.sh; e.o_sw = g.sw; e.o_oy = g.oy; e.o_ox = g.ox;
-  e.o_Hq = g.Hq; e.o_Wq = g.Wq; e.o_H = g.H; e.o_W = g.W;
-  e.o_plane = g.plane_stride;
+  e.o_H = g.H; e.o_W = g.W;
+  e.o_plane = g.plane_stride; e.o_rstride = g.rstride; e.o_ustride = g.ustride;
 }
 
 EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const float* bias_const, const float* tftab,
@@ -345,9 +345,9 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     const GemmLayerDev& D = net.layers[i];
     GemmDev g;
     memset(&g, 0, sizeof g);
-    long long M = (long long)units * L.Hq * L.Wq;
-    if (M > 0x7fffffffLL) return fail(ctx, NHANS_ERR_ARG, "too many rows in one pass");
-    g.M = (int)M; g.N = L.N; g.BN = L.BN; g.num_kb = (int)L.kb.size(); g.num_groups = (int)L.groups.size(); g.groups = D.groups;
+    long long M = (long long)units * L.Ho * L.Wq;
+    if ((long long)P.capacity * L.Ho * L.Wq > 0x7fffffffLL) return fail(ctx, NHANS_ERR_ARG, "too many rows in one pass");
+    g.M = (int)M; g.plane_pitch = P.capacity * L.Wq; g.plane_rows = units * L.Wq; g.N = L.N; g.BN = L.BN; g.num_kb = (int)L.kb.size(); g.num_groups = (int)L.groups.size(); g.groups = D.groups;
     g.Hq = L.Hq; g.Wq = L.Wq; g.Ho = L.Ho; g.Wo = L.Wo;
     g.units = ut;
     g.epi = make_epi(net, L.epi, L.out, D.bias, D.tftab, D.res_scale, D.r1_vec, raw, cond_table, out_f32);

@@ -166,7 +166,6 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
   const EpiDev& e = p.epi;
   const int MT = cfg.mt;
   const int q = ew & 3, half = ew >> 2;
-  const int hw = p.Hq * p.Wq;
   uint8_t* epi_base = reinterpret_cast<uint8_t*>(ctrl) + kCtrlBytes + ew * kEpiWarpBytes;
   uint4* stage = reinterpret_cast<uint4*>(epi_base);                 // [32 rows][4 x 16 B], XOR swizzled
   int4* meta = reinterpret_cast<int4*>(epi_base + 32 * 64);          // [32] {pixel, (ho << 16) | wo, utt, raw bits}
@@ -201,18 +200,20 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
       release_acc(acc);
       continue;
     }
-    const int tile_m0 = (tile / n_tiles) * (MT * sub_rows) + (int)rank * 128;
+    // tile -> (row chunk, image row) with the image row fastest (kernels.h GemmDev)
+    const int mtile = tile / n_tiles;
+    const int tchunk = mtile / p.Ho, ho = mtile - tchunk * p.Ho;
+    const int local0 = tchunk * (MT * sub_rows) + (int)rank * 128;      // first row of this CTA within the plane
+    const int tile_m0 = ho * p.plane_pitch + local0;
     // metadata of the row this thread owns in slot v (its TMEM lane)
     auto slot_meta = [&](int v) -> int4 {
       if (v >= NV) return make_int4(-1, 0, 0, 0);
       const int i = kPair ? (v >> 1) : v, j = kPair ? (v & 1) : 0;
-      const int m = tile_m0 + i * sub_rows + q * 32 + lane;
-      if (m >= p.M) return make_int4(-1, 0, 0, 0);
-      const int unit = m / hw;
-      const int rem = m - unit * hw;
-      const int ho = rem / p.Wq;
-      int wo = rem - ho * p.Wq;
-      if (ho >= p.Ho || wo >= p.Wo) return make_int4(-1, 0, 0, 0);
+      const int r = local0 + i * sub_rows + q * 32 + lane;
+      if (r >= p.plane_rows) return make_int4(-1, 0, 0, 0);
+      const int unit = r / p.Wq;
+      int wo = r - unit * p.Wq;
+      if (wo >= p.Wo) return make_int4(-1, 0, 0, 0);
       if (kPair) {
         wo = 2 * wo + j;
         if (wo >= e.pair_W) return make_int4(-1, 0, 0, 0);
@@ -231,7 +232,7 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
       } else {
         const int y = ho + e.o_oy, x = wo + e.o_ox;
         const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
-        pix = (int)(plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw));
+        pix = (int)(plane * e.o_plane + unit * e.o_ustride + (y / e.o_sh) * e.o_rstride + (x / e.o_sw));
       }
       return make_int4(pix, (ho << 16) | wo, utt, __float_as_int(rawv));
     };
@@ -241,7 +242,7 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
     for (int v = 0; v < NV; ++v) {
       const int i = kPair ? (v >> 1) : v;
       const int m0 = tile_m0 + i * sub_rows;
-      if (m0 >= p.M) break;
+      if (local0 + i * sub_rows >= p.plane_rows) break;
       const int4 md_cur = md_next;
       md_next = slot_meta(v + 1);             // its loads are in flight while slot v is processed
       __syncwarp();
@@ -391,7 +392,6 @@ __device__ __forceinline__ void epilogue_warp_row(Ctrl* ctrl, const GemmDev& p, 
   const EpiDev& e = p.epi;
   const int MT = cfg.mt;
   const int q = ew & 3, half = ew >> 2;
-  const int hw = p.Hq * p.Wq;
   const int NV = kPair ? 2 * MT : MT;
   const int vcols = kPair ? e.n_real : p.BN;
   const int tab_C = kPair ? e.n_real : p.N;
@@ -422,23 +422,24 @@ __device__ __forceinline__ void epilogue_warp_row(Ctrl* ctrl, const GemmDev& p, 
       release_acc(acc);
       continue;
     }
-    const int tile_m0 = (tile / n_tiles) * (MT * sub_rows) + (int)rank * 128;
+    const int mtile = tile / n_tiles;
+    const int tchunk = mtile / p.Ho, ho = mtile - tchunk * p.Ho;      // image row fastest (kernels.h GemmDev)
+    const int local0 = tchunk * (MT * sub_rows) + (int)rank * 128;
+    const int tile_m0 = ho * p.plane_pitch + local0;
     bool waited = false;
     bool row_ok = false;
-    int unit = 0, ho = 0, wb = 0, utt = 0;
+    int unit = 0, wb = 0, utt = 0;
 #pragma unroll 1
     for (int v = 0; v < NV; ++v) {
       const int i = kPair ? (v >> 1) : v, j = kPair ? (v & 1) : 0;
       const int m0 = tile_m0 + i * sub_rows;
-      if (m0 >= p.M) break;
+      if (local0 + i * sub_rows >= p.plane_rows) break;
       const int m = m0 + q * 32 + lane;
       if (!kPair || j == 0) {                 // the row this thread owns in sub-tile i
-        row_ok = m < p.M;
-        unit = m / hw;
-        const int rem = m - unit * hw;
-        ho = rem / p.Wq;
-        wb = rem - ho * p.Wq;
-        row_ok = row_ok && ho < p.Ho && wb < p.Wo;
+        const int r = local0 + i * sub_rows + q * 32 + lane;
+        unit = r / p.Wq;
+        wb = r - unit * p.Wq;
+        row_ok = r < p.plane_rows && wb < p.Wo;
         utt = row_ok ? p.units.utt[unit] : 0;
       }
       const int wo = kPair ? 2 * wb + j : wb;
@@ -457,7 +458,7 @@ __device__ __forceinline__ void epilogue_warp_row(Ctrl* ctrl, const GemmDev& p, 
         } else {
           const int y = ho + e.o_oy, x = wo + e.o_ox;
           const int plane = (y % e.o_sh) * e.o_sw + (x % e.o_sw);
-          pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(y / e.o_sh) * e.o_Wq + (x / e.o_sw);
+          pix = plane * e.o_plane + unit * e.o_ustride + (y / e.o_sh) * e.o_rstride + (x / e.o_sw);
         }
         o_out = (size_t)pix * e.out_C + n0;
         o_bias = (size_t)utt * e.bias_stride + n0;
@@ -582,7 +583,7 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int MT = cfg.mt;                          // sub-tiles of 128 rows per CTA tile
   const int n_tiles = p.N / p.BN;
   const int tile_rows = (MT * 128) << cta_shift;
-  const int m_tiles = (p.M + tile_rows - 1) / tile_rows;
+  const int m_tiles = p.Ho * ((p.plane_rows + tile_rows - 1) / tile_rows);
   const int num_tiles = m_tiles * n_tiles;
   const int num_groups = p.num_groups;
 
@@ -651,7 +652,9 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // (whole warp runs the loop; one elected lane issues the TMA - keeps the control flow warp-uniform)
     uint32_t slot = 0, phase = 0;
     for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift) {
-      const int m0 = (tile / n_tiles) * tile_rows + (int)rank * 128;
+      const int mtile = tile / n_tiles;
+      const int tchunk = mtile / p.Ho;
+      const int m0 = (mtile - tchunk * p.Ho) * p.plane_pitch + tchunk * tile_rows + (int)rank * 128;
       for (int g = 0; g < num_groups; ++g) {
         const int row_off = ctrl->groups[g].row_off, col = ctrl->groups[g].col, map = ctrl->groups[g].map;
         for (int i = 0; i < MT; ++i) {
@@ -813,7 +816,7 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   if ((desc_mode >> 1) & 7) { cfg.il = (desc_mode >> 1) & 7; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
   if (cfg.nb < 4) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight
   const int tile_rows = (cfg.mt * 128) << cta2;
-  const int tiles = ((p.M + tile_rows - 1) / tile_rows) * (p.N / p.BN);
+  const int tiles = p.Ho * ((p.plane_rows + tile_rows - 1) / tile_rows) * (p.N / p.BN);
   int grid = tiles < (n_sm >> cta2) ? tiles : (n_sm >> cta2);
   grid <<= cta2;                              // CTA pairs: two CTAs per tile
   const EpiDev& e = p.epi;

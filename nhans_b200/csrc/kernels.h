@@ -38,8 +38,8 @@ struct EpiDev {
   // output grid (plan.h Grid)
   __half* out;
   int out_C;
-  int o_mode, o_sh, o_sw, o_oy, o_ox, o_Hq, o_Wq, o_H, o_W;
-  long long o_plane;
+  int o_mode, o_sh, o_sw, o_oy, o_ox, o_H, o_W;
+  long long o_plane, o_rstride, o_ustride;   // pixel = plane * o_plane + (y / sh) * o_rstride + unit * o_ustride + x / sw
   float* out_f32;
 };
 
@@ -62,7 +62,12 @@ struct GemmCfg {              // chosen by the host per layer shape
 };
 
 struct GemmDev {
-  int M;                    // compute rows = units * Hq * Wq
+  // compute space (plan.h): row m = ho * plane_pitch + unit * Wq + wo; only ho < Ho and rows < plane_rows of each
+  // plane are enumerated: tile -> (chunk t, plane ho) with ho fastest, so that the kh taps of a pixel are read by
+  // tiles that run close together in time (L2 reuse of the activations)
+  int M;                    // rows enumerated = Ho * plane_rows
+  int plane_pitch;          // capacity * Wq
+  int plane_rows;           // units * Wq
   int N, BN;
   int num_kb;               // k-blocks (64 wide) of the packed weights
   int num_groups;

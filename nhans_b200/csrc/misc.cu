@@ -67,7 +67,7 @@ direct_conv64_kernel(const DirectDev p) {
   const int utt = p.units_tab.utt ? p.units_tab.utt[unit] : 0;
   const int yy = ho + e.o_oy, xx = wo + e.o_ox;
   const int plane = (yy % e.o_sh) * e.o_sw + (xx % e.o_sw);
-  const long long pix = plane * e.o_plane + (long long)unit * e.o_Hq * e.o_Wq + (long long)(yy / e.o_sh) * e.o_Wq + (xx / e.o_sw);
+  const long long pix = plane * e.o_plane + unit * e.o_ustride + (yy / e.o_sh) * e.o_rstride + (xx / e.o_sw);
   const int lane = threadIdx.x & 31;
   float* st = s_stage + (threadIdx.x >> 5) * (32 * kDirectPitch);
   long long* s_pix = reinterpret_cast<long long*>(s_meta) + (threadIdx.x >> 5) * 32;
@@ -183,7 +183,7 @@ direct_conv_mma_kernel(const DirectDev p, const int segs) {
       if (tab == 1) add_half8(bias, __ldg(reinterpret_cast<const uint4*>(e.ttab16 + ho * 64 + cg)));
     }
     const int yy = ho + e.o_oy;
-    const long long row_pix = (long long)unit * e.o_Hq * e.o_Wq + (long long)(yy / e.o_sh) * e.o_Wq;
+    const long long row_pix = unit * e.o_ustride + (yy / e.o_sh) * e.o_rstride;
     const int plane_y = (yy % e.o_sh) * e.o_sw;
     for (int seg = 0; seg < segs; ++seg) {
       const int wo0 = seg * 16;

@@ -148,15 +148,17 @@ int32_t tap_offset(const Grid& g, int dy, int dx) {
   int y0 = dy + g.oy, x0 = dx + g.ox;
   int qy = floordiv(y0, g.sh), qx = floordiv(x0, g.sw);
   int py = y0 - qy * g.sh, px = x0 - qx * g.sw;
-  int64_t off = (int64_t)(py * g.sw + px) * g.plane_stride + (int64_t)qy * g.Wq + qx;
+  int64_t off = (int64_t)(py * g.sw + px) * g.plane_stride + (int64_t)qy * g.rstride + qx;
   if (off > INT32_MAX || off < INT32_MIN) throw std::runtime_error("tap offset overflows int32");
   return (int32_t)off;
 }
 
-Grid make_grid(int buf, int H, int W, int C, int sh, int sw, int oy, int ox, int Hq, int Wq, int cap) {
+Grid make_grid(int buf, int H, int W, int C, int sh, int sw, int oy, int ox, int Hq, int Wq, int cap, bool unit_major = false) {
   Grid g;
   g.buf = buf; g.H = H; g.W = W; g.C = C;
   g.sh = sh; g.sw = sw; g.oy = oy; g.ox = ox; g.Hq = Hq; g.Wq = Wq;
+  if (unit_major) { g.ustride = (int64_t)Hq * Wq; g.rstride = Wq; }
+  else            { g.ustride = Wq; g.rstride = (int64_t)cap * Wq; }
   g.plane_stride = (int64_t)cap * Hq * Wq;
   g.pixels = g.plane_stride * sh * sw;
   return g;
@@ -491,8 +493,9 @@ static std::string grid_json(const Grid& g) {
   char b[512];
   snprintf(b, sizeof b,
            "{\"buf\":%d,\"C\":%d,\"H\":%d,\"W\":%d,\"mode\":%d,\"sh\":%d,\"sw\":%d,\"oy\":%d,\"ox\":%d,\"Hq\":%d,"
-           "\"Wq\":%d,\"plane_stride\":%lld,\"pixels\":%lld}",
-           g.buf, g.C, g.H, g.W, g.mode, g.sh, g.sw, g.oy, g.ox, g.Hq, g.Wq, (long long)g.plane_stride, (long long)g.pixels);
+           "\"Wq\":%d,\"rstride\":%lld,\"ustride\":%lld,\"plane_stride\":%lld,\"pixels\":%lld}",
+           g.buf, g.C, g.H, g.W, g.mode, g.sh, g.sw, g.oy, g.ox, g.Hq, g.Wq, (long long)g.rstride, (long long)g.ustride,
+           (long long)g.plane_stride, (long long)g.pixels);
   return b;
 }
 
@@ -588,7 +591,7 @@ NetPlan build_tower_plan(const WeightMap& w, int capacity) {
   std::vector<BlockSpec> blocks = {                      // main.py:192-197
       {"embedding/noise_resblock1_1", 8, 4, 3, 2, 64},  {"embedding/noise_resblock2_1", 8, 4, 3, 2, 128},
       {"embedding/noise_resblock3_1", 4, 4, 1, 1, 256}, {"embedding/noise_resblock4_1", 4, 4, 1, 2, 512}};
-  Grid pool = make_grid(-1, 23, 26, 512, 1, 1, 0, 0, 23, 26, capacity);
+  Grid pool = make_grid(-1, 23, 26, 512, 1, 1, 0, 0, 23, 26, capacity, true);   // unit-major for mean_pool_kernel
   build_blocks(&B, blocks, kCtxFrames, kBins, kCtxFrames, 0, pool);
   B.plan.pool_buf = B.plan.gemm.back().out.buf;
   B.plan.pool_pixels = 23 * 26;

@@ -34,9 +34,16 @@ constexpr int kTileK = 64;
 
 // An fp16 activation tensor [n][H][W][C] stored as a padded, optionally phase-split pixel grid:
 // logical pixel (n, h, w) -> padded (y, x) = (h + oy, w + ox) -> phase plane (y % sh) * sw + (x % sw)
-// at linear pixel n * Hq * Wq + (y / sh) * Wq + (x / sw).  Everything that is not a logical pixel
-// is zero for the lifetime of the buffer (it is never written), which is what implements the
-// convolution padding.  mode 1 is the head layout [n][w][h][c] read by last_conv as a plain GEMM.
+// at linear pixel plane * plane_stride + (y / sh) * rstride + n * ustride + (x / sw).
+// Row-major over the image row first ("row-outer": rstride = cap * Wq, ustride = Wq): all units' copies of image
+// row y are contiguous, so a vertical filter tap is the constant offset cap * Wq and the rows above the first /
+// below the last image row of a plane are either outside the tensor (TMA zero-fills them) or the plane's spare
+// rows (Hq - rows used).  A GEMM therefore only enumerates real output rows, no margin rows (they cost 5-17 % of
+// the MMA work in a unit-major layout).  Horizontally a row segment holds W + pad pixels (shared left / right
+// margin).  Everything that is not a logical pixel is zero for the lifetime of the buffer (it is never written),
+// which is what implements the convolution padding.  The tower's final map uses the unit-major variant
+// (ustride = Hq * Wq, rstride = Wq) because the pooling kernel wants a unit's pixels together; mode 1 is the
+// head layout [n][w][h][c] read by last_conv as a plain GEMM.
 struct Grid {
   int buf = -1;
   int C = 0;
@@ -44,7 +51,8 @@ struct Grid {
   int mode = 0;
   int sh = 1, sw = 1, oy = 0, ox = 0;
   int Hq = 1, Wq = 1;
-  int64_t plane_stride = 0;       // pixels between phase planes
+  int64_t rstride = 1, ustride = 1; // pixels between image rows / between units
+  int64_t plane_stride = 0;       // pixels between phase planes (= cap * Hq * Wq)
   int64_t pixels = 0;             // total pixels of the buffer (all planes)
 };
 
@@ -52,7 +60,7 @@ inline int64_t grid_pixel(const Grid& g, int64_t n, int h, int w) {
   if (g.mode == 1) return (n * g.W + w) * g.H + h;
   int y = h + g.oy, x = w + g.ox;
   int plane = (y % g.sh) * g.sw + (x % g.sw);
-  return plane * g.plane_stride + n * (int64_t)g.Hq * g.Wq + (int64_t)(y / g.sh) * g.Wq + (x / g.sw);
+  return plane * g.plane_stride + (int64_t)(y / g.sh) * g.rstride + n * g.ustride + (x / g.sw);
 }
 
 struct KBlock {                   // one 64-wide k-block of a GemmLayer
@@ -100,7 +108,7 @@ struct Epilogue {
 
 struct GemmLayer {
   std::string name;
-  int Hq = 1, Wq = 1, Ho = 1, Wo = 1;     // compute space: m = (n * Hq + ho) * Wq + wo, valid ho < Ho, wo < Wo
+  int Hq = 1, Wq = 1, Ho = 1, Wo = 1;     // compute space: m = (ho * cap + n) * Wq + wo, ho < Ho, valid wo < Wo (Hq: rows stored per plane)
   int a_buf[2] = {-1, -1};
   int a_rowlen[2] = {0, 0};               // elements per row of the 2-D view TMA reads (channels, or K for the head)
   int N = 0, BN = 0;                      // N padded to a multiple of 16; BN = columns per CTA tile

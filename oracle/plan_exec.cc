@@ -109,17 +109,20 @@ void run_net(Net& net, int units_n, const Units& units, const float* raw, const 
   for (size_t li = 0; li < P.gemm.size(); ++li) {
     const GemmLayer& L = P.gemm[li];
     const std::vector<float>& wt = net.wt[li];
-    const long long M = (long long)units_n * L.Hq * L.Wq;
+    // compute space (plan.h): m = (ho * capacity + unit) * Wq + wo, only real output rows ho < Ho are enumerated
+    const long long pitch = (long long)P.capacity * L.Wq;
+    const long long per_plane = (long long)units_n * L.Wq;
     long long rows[2] = {0, 0};
     for (int a = 0; a < 2; ++a)
       if (L.a_buf[a] >= 0) rows[a] = (long long)P.bufs[L.a_buf[a]].pixels * P.bufs[L.a_buf[a]].C / L.a_rowlen[a];
 #pragma omp parallel for schedule(dynamic, 32)
-    for (long long m = 0; m < M; ++m) {
-      const int hw = L.Hq * L.Wq;
-      const int unit = (int)(m / hw);
-      const int rem = (int)(m % hw);
-      const int ho = rem / L.Wq, wo = rem % L.Wq;
-      if (ho >= L.Ho || wo >= L.Wo) continue;
+    for (long long idx = 0; idx < (long long)L.Ho * per_plane; ++idx) {
+      const int ho = (int)(idx / per_plane);
+      const long long rem = idx - (long long)ho * per_plane;
+      const int unit = (int)(rem / L.Wq);
+      const int wo = (int)(rem - (long long)unit * L.Wq);
+      const long long m = (long long)ho * pitch + rem;
+      if (wo >= L.Wo) continue;
       std::vector<float> acc(L.N, 0.f);
       for (const KGroup& g : L.groups) {
         for (int t = 0; t < g.ntaps; ++t) {

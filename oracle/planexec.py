@@ -97,5 +97,5 @@ def grid_gather(grid, flat, n_units):
         y = h + grid["oy"]
         x = w + grid["ox"]
         plane = (y % grid["sh"]) * grid["sw"] + (x % grid["sw"])
-        pix = plane * grid["plane_stride"] + n * grid["Hq"] * grid["Wq"] + (y // grid["sh"]) * grid["Wq"] + (x // grid["sw"])
+        pix = plane * grid["plane_stride"] + n * grid["ustride"] + (y // grid["sh"]) * grid["rstride"] + (x // grid["sw"])
     return flat[pix]
