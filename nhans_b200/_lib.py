@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libnhans_b200.so")
+SO_PATH = os.environ.get("NHANS_B200_LIB") or os.path.join(_HERE, "libnhans_b200.so")     # override: A/B builds
 
 # every symbol include/nhans_b200.h declares (tests check the library exports each of them)
 SYMBOLS = [

@@ -142,7 +142,7 @@ __device__ __forceinline__ void add_half8(float (&b)[8], const uint4 t) {
 }
 
 template <int KSTEPS>
-__global__ void __launch_bounds__(kMmaWarps * 32)
+__global__ void __launch_bounds__(kMmaWarps * 32)     // 80 registers; capping them for 7-8 blocks/SM spills and is 15 % slower
 direct_conv_mma_kernel(const DirectDev p, const int segs) {
   extern __shared__ float4 s_b[];                      // [ksteps][8 n-tiles][32 lanes] {b0_hi, b1_hi, b0_lo, b1_lo}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -10,6 +10,6 @@ B="python bench.py --steps 1 --warmup 1 --utts 32 --no-cpu-baseline"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/${TAG}_launches.csv $B > $OUT/${TAG}_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_shift -s 30 -c 17 -f -o /tmp/${TAG}_gemm $B > $OUT/${TAG}_gemm.log 2>&1
 ncu -i /tmp/${TAG}_gemm.ncu-rep --page raw --csv > $OUT/${TAG}_gemm_raw.csv 2>> $OUT/${TAG}_gemm.log
-timeout 600 ncu --set full --clock-control none -k regex:'stft_kernel|istft_kernel|direct_conv_mma' -s 3 -c 12 -f -o /tmp/${TAG}_dsp python bench.py --steps 1 --warmup 1 --utts 256 --no-cpu-baseline > $OUT/${TAG}_dsp.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:'stft_kernel|istft_kernel' -c 8 -f -o /tmp/${TAG}_dsp python bench.py --steps 1 --warmup 1 --utts 256 --no-cpu-baseline > $OUT/${TAG}_dsp.log 2>&1
 ncu -i /tmp/${TAG}_dsp.ncu-rep --page raw --csv > $OUT/${TAG}_dsp_raw.csv 2>> $OUT/${TAG}_dsp.log
 ls -la $OUT | tail -12

@@ -122,7 +122,7 @@ if os.path.exists(dp):
             "sm__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__registers_per_thread"]
     ki = hdr.index("Kernel Name")
     with open(os.path.join(P, outp + "_dsp_ncu.txt"), "w") as f:
-        f.write("ncu --set full -k regex:stft_kernel|istft_kernel|direct_conv_mma -s 3 -c 12: bench.py --utts 256 (256 x 4 s; %s)\n" % note)
+        f.write("ncu --set full -k regex:stft_kernel|istft_kernel -c 8: bench.py --utts 256 (256 x 4 s; %s)\n" % note)
         for row in rows:
             parts = [short(row[ki])]
             for w in want:
