@@ -10,13 +10,17 @@ A restatement, in numpy / torch-CPU, of the reference's inference path:
   * reconstruction ............. SN/apply.py:189-204 (tf.signal.inverse_stft + inverse_stft_window_fn)
   * mini-batch loop ............ SN/apply.py:440-454 (mb = 100)
   * post-mix outputs ........... SN/apply.py:456-472
+  * apply_demo / eval reader ... SN/apply.py:56-139, 212-337; SN/reader.py:131-223, 398-420; SN/main.py:243-246
 
 PARITY UNPINNED for the network arithmetic: the reference cannot run here (TensorFlow is not
 installed, the trained blobs are git-LFS pointers, the repo ships no tests or golden vectors —
-SURVEY.md F4/F5, §8c).  What *is* pinned: the variable inventory against the reference's own
-checkpoint ``.index`` files (tests/golden/ckpt_index_*.json), the DSP against numpy.fft
-definitions and the STFT->iSTFT identity, the conv/padding rule against torch's conv2d, and the
-window/frame indexing identities of SURVEY.md §4.
+SURVEY.md F4/F5, §8c).  What *is* pinned against reference-produced artefacts: the variable
+inventory against the reference's own checkpoint ``.index`` files (tests/golden/ckpt_index_*.json);
+the mixing arithmetic (domixing: the target / noise scaling quirk and the SNR convention) against the
+13 wav sets the reference's evaluate() wrote under DEMO_N-HANS/ (tests/golden/demo_relations.npz);
+the trim / output-length rule against audio_examples/exp{1,2}_{noisy,denoised}.wav.  Pinned against
+definitions only: the DSP against numpy.fft and the STFT->iSTFT identity, the conv/padding rule
+against torch's conv2d, the window/frame indexing identities of SURVEY.md §4.
 
 Two modes of ``apply_snc``: ``faithful=True`` follows the reference structure exactly (windows
 and tiled contexts materialised, both embedding towers evaluated for every window of every
