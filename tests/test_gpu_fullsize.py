@@ -83,3 +83,23 @@ def test_cfg4_separator_10s(weights_ss, oracle_ss):
     ref = O.apply_arrays(oracle_ss, *base[0])
     assert _snr(ref, res["f32"][0]) >= 40.0
     eng.close()
+
+
+def test_cfg5_shard_512x10s(big_sn):
+    """configs[4]: the utterance-sharded sweep gives each of 8 GPUs 1024 x 10 s clips; half such a shard (512 x 10 s,
+    0.5 M windows, 250 passes) goes through one nhans_enhance_batch call here.  Copies must come back bit-identical
+    wherever they sit, outputs have the trimmed length, and a clip processed alone gives the same samples."""
+    base_m = [synth.mixture(10.0, 60 + u) for u in range(4)]
+    base_n = [synth.noise_clip(60 + u) for u in range(4)]
+    order = [(3 * u + 1) % 4 for u in range(512)]
+    res = big_sn.enhance([base_m[i] for i in order], None, [base_n[i] for i in order], want_f32=False)
+    first = {}
+    for u, i in enumerate(order):
+        assert len(res["i16"][u]) == O.trim_len(160000)
+        if i in first:
+            assert np.array_equal(res["i16"][u], res["i16"][first[i]])
+        else:
+            first[i] = u
+    solo = big_sn.enhance([base_m[2]], None, [base_n[2]], want_f32=False)
+    assert np.array_equal(solo["i16"][0], res["i16"][first[2]])
+    assert np.abs(res["i16"][first[2]].astype(np.int32)).max() > 1000      # not silence
