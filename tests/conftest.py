@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """A fresh checkout has no binaries: build the CUDA library (nvcc cross-compiles without a GPU) and the
+    test-only plan interpreter once per session, like __graft_entry__.build() does."""
+    import subprocess
+    if not os.path.exists(os.path.join(ROOT, "nhans_b200", "libnhans_b200.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "nhans_b200", "csrc"), "-j8"])
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_build", "libplanexec.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    yield
+
+
 def _has_gpu():
     try:
         from nhans_b200.engine import Engine
