@@ -62,6 +62,8 @@ struct NetDev {
   uint16_t *first_ttab16 = nullptr, *first_ftab16 = nullptr;
   float *Pa = nullptr, *Pb = nullptr, *c = nullptr;
   int *u_frame = nullptr, *u_lo = nullptr, *u_hi = nullptr, *u_utt = nullptr;
+  float* convC = nullptr;           // main net: per-frame first-convolution table (kernels.h FrameConvDev)
+  long long crow_cap = 0;
   std::vector<void*> allocs;
   bool ready = false;
 };
@@ -178,6 +180,15 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
     net.bufs[i] = reinterpret_cast<__half*>(p);
   }
   int rc;
+  if (P.cond.n_cols > 0 && !getenv("NHANS_NO_FRAMECONV")) {
+    // main net: room for the frames of one pass plus 34 virtual frames per utterance (utterances of >= 17 frames on
+    // average; a pass of shorter ones falls back to the per-window kernel)
+    net.crow_cap = 3LL * P.capacity + 64;
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)4 * net.crow_cap * kBins * 64 * sizeof(float)));
+    net.allocs.push_back(p);
+    net.convC = reinterpret_cast<float*>(p);
+  }
   if ((rc = upload(ctx, net, P.first.w, &net.first_w))) return rc;
   if ((rc = upload(ctx, net, P.first.epi.bias, &net.first_bias))) return rc;
   if ((rc = upload(ctx, net, P.first.epi.tftab, &net.first_tftab))) return rc;
@@ -320,8 +331,16 @@ EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const flo
   return e;
 }
 
+struct PassInfo {                   // which frames / utterances a pass of the mask network touches
+  long long w0;                     // first window (= global frame index of its centre)
+  int u_first, u_last;
+  const long long* d_frame_offs;
+  int U;
+};
+
 // Runs `units` windows / context rows whose unit tables are already filled.
-int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const float* cond_table, float* out_f32) {
+int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const float* cond_table, float* out_f32,
+            const PassInfo* pass = nullptr) {
   const NetPlan& P = net.plan;
   UnitTable ut{net.u_frame, net.u_lo, net.u_hi, net.u_utt};
   {
@@ -338,7 +357,29 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     d.epi.ftab16 = reinterpret_cast<const __half*>(net.first_ftab16);
     d.epi.tab_H = D.Ho; d.epi.tab_W = D.Wo;
     ProfScope ps(ctx, 3, 2.0 * D.macs_per_unit * units, 0);
-    CK(launch_direct_conv(ctx->stream, d));
+    bool done = false;
+    if (pass && net.convC && D.kh == 4 && D.kw == 4 && D.sh == 1 && D.sw == 1 && D.pt == 1 && D.pl == 1 && D.Hin == kWinFrames &&
+        D.Ho == kWinFrames && D.raw_oh == -(kWinFrames / 2) && D.N == 64) {
+      FrameConvDev f;
+      memset(&f, 0, sizeof f);
+      f.raw = raw; f.frame_offs = pass->d_frame_offs;
+      f.u_first = pass->u_first; f.u_last = pass->u_last;
+      f.crow0 = pass->w0 + 34LL * pass->u_first;
+      const long long last = pass->w0 + units - 1 + 34LL * pass->u_last + (kWinFrames - 1);
+      f.rows = (int)(last - f.crow0 + 1);
+      f.crow_cap = net.crow_cap;
+      f.w = net.first_w;
+      f.bias = d.epi.bias; f.bias_stride = d.epi.bias_stride; f.ftab16 = d.epi.ftab16;
+      f.C = net.convC;
+      if (f.rows <= net.crow_cap) {
+        // (expanding the pass in slices so that a slice's table stays L2-resident was measured: no gain)
+        CK(launch_frame_conv(ctx->stream, f));
+        CK(launch_window_expand(ctx->stream, d, net.convC, f.crow0, net.crow_cap, 0, units));
+        ctx->launches += 1;
+        done = true;
+      }
+    }
+    if (!done) CK(launch_direct_conv(ctx->stream, d));
   }
   for (size_t i = 0; i < P.gemm.size(); ++i) {
     const GemmLayer& L = P.gemm[i];
@@ -385,8 +426,8 @@ int run_tower(nhans_ctx* ctx, const float* ctx_logmag, int R, float* emb) {
 }
 
 // Mask network over all frames (device logmag rows) -> denoised rows.
-int run_masknet(nhans_ctx* ctx, const float* logmag, const long long* d_frame_offs, int U, long long total_frames,
-                const float* cond_table, float* den) {
+int run_masknet(nhans_ctx* ctx, const float* logmag, const long long* d_frame_offs, const long long* h_frame_offs, int U,
+                long long total_frames, const float* cond_table, float* den) {
   NetDev& net = ctx->main_net;
   const int cap = net.plan.capacity;
   if (total_frames > 0x7fffffffLL) return fail(ctx, NHANS_ERR_ARG, "too many frames in one batch");
@@ -394,7 +435,12 @@ int run_masknet(nhans_ctx* ctx, const float* logmag, const long long* d_frame_of
     const int n = (int)std::min<long long>(cap, total_frames - w0);
     CK(launch_units_main(ctx->stream, d_frame_offs, U, (int)w0, n, net.u_frame, net.u_lo, net.u_hi, net.u_utt));
     ctx->launches += 1;
-    int rc = run_net(ctx, net, n, logmag, cond_table, den + (size_t)w0 * kBins);
+    PassInfo pi;
+    pi.w0 = w0; pi.d_frame_offs = d_frame_offs; pi.U = U;
+    // utterances of the first / last window of the pass: largest u with frame_offs[u] <= frame
+    pi.u_first = (int)(std::upper_bound(h_frame_offs, h_frame_offs + U + 1, w0) - h_frame_offs) - 1;
+    pi.u_last = (int)(std::upper_bound(h_frame_offs, h_frame_offs + U + 1, w0 + n - 1) - h_frame_offs) - 1;
+    int rc = run_net(ctx, net, n, logmag, cond_table, den + (size_t)w0 * kBins, &pi);
     if (rc) return rc;
   }
   return 0;
@@ -699,7 +745,7 @@ int nhans_masknet(nhans_ctx* ctx, const float* logmag, const int64_t* frame_offs
   CK(cudaMemcpyAsync(ctx->tmp[3].p, emb_b, (size_t)U * 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(launch_cond_table(ctx->stream, ctx->tmp[2].as<float>(), 512, ctx->tmp[3].as<float>(), 512, U, ctx->main_net.Pa,
                        ctx->main_net.Pb, ctx->main_net.c, n_cols, ctx->tmp[4].as<float>()));
-  if ((rc = run_masknet(ctx, ctx->tmp[0].as<float>(), ctx->tmp[5].as<long long>(), U, total, ctx->tmp[4].as<float>(),
+  if ((rc = run_masknet(ctx, ctx->tmp[0].as<float>(), ctx->tmp[5].as<long long>(), fo.data(), U, total, ctx->tmp[4].as<float>(),
                         ctx->tmp[1].as<float>())))
     return rc;
   CK(cudaMemcpyAsync(denoised, ctx->tmp[1].p, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -866,8 +912,8 @@ int nhans_run(nhans_ctx* ctx) {
     CK(launch_cond_table(ctx->stream, emb_a, stride_a, b.emb_b.as<float>(), 512, U, ctx->main_net.Pa, ctx->main_net.Pb,
                          ctx->main_net.c, n_cols, b.cond.as<float>()));
   }
-  if ((rc = run_masknet(ctx, b.logmag.as<float>(), b.d_frame_offs.as<long long>(), U, b.total_frames, b.cond.as<float>(),
-                        b.den.as<float>())))
+  if ((rc = run_masknet(ctx, b.logmag.as<float>(), b.d_frame_offs.as<long long>(), b.frame_offs.data(), U, b.total_frames,
+                        b.cond.as<float>(), b.den.as<float>())))
     return rc;
   {
     ProfScope ps(ctx, 2, 0, 3.0 * sbytes + 6.0 * b.total_out);

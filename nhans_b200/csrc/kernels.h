@@ -97,6 +97,32 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
                         const CUtensorMap& mapB, const CUtensorMap& mapBhalf, const GemmDev& p, int desc_mode);
 cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p);
 
+// First convolution of the mask network, computed once per FRAME instead of once per (window, row): the 35-frame
+// windows of one utterance are shifted copies of the same spectrogram, so conv(x)[window n, row h] depends only on
+// the frame n - 17 + h - except for which kernel rows fall outside the window (rows h = 0, 33, 34), which gives four
+// variants per frame.  frame_conv fills C[variant][crow][201][64] (fp32 FMA) for the frames a pass touches; crow =
+// frame + 34 * utterance + row indexes the zero-extended utterance (17 virtual frames on either side), and the
+// conditioning bias of the utterance and the frequency embedding F[w] are folded in (a C row belongs to one
+// utterance).  window_expand then writes h1[n][h][w][:] = relu(C[variant(h)][crow(n) + h][w][:] + T[h]) in fp16:
+// 35x fewer multiply-adds than the per-window kernel, what remains is the 1.8 GB store stream of a pass.
+struct FrameConvDev {
+  const float* raw;            // [frames][201] log-magnitude
+  const long long* frame_offs; // [U + 1] device
+  int u_first, u_last;         // utterances the pass touches
+  long long crow0;             // first C row of the pass = first window + 34 * u_first
+  int rows;                    // C rows to fill
+  long long crow_cap;          // rows per variant plane of C
+  const float* w;              // [16][64] taps (batch-norm scale folded)
+  const float* bias;           // per-utterance bias rows (EpiDev::bias / bias_stride)
+  int bias_stride;
+  const __half* ftab16;        // [201][64] frequency embedding or null
+  float* C;
+};
+cudaError_t launch_frame_conv(cudaStream_t s, const FrameConvDev& p);
+// windows [unit0, unit1) of the pass
+cudaError_t launch_window_expand(cudaStream_t s, const DirectDev& d, const float* C, long long crow0, long long crow_cap, int unit0,
+                                 int unit1);
+
 // bias_utt[u][j] = emb_a[u] . Pa[:, j] + emb_b[u] . Pb[:, j] + c[j]
 // (stride 0 broadcasts one embedding row, e.g. the cached Silent.wav embedding of apply_denoiser)
 cudaError_t launch_cond_table(cudaStream_t s, const float* emb_a, int stride_a, const float* emb_b, int stride_b, int U, const float* Pa,

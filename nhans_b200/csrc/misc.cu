@@ -258,6 +258,130 @@ direct_conv_mma_kernel(const DirectDev p, const int segs) {
   }
 }
 
+// ---- first convolution per frame + window expansion (kernels.h FrameConvDev) ----
+constexpr int kVirt = 17;                               // virtual frames on either side of an utterance (window half)
+
+// grid: rows; block 256: items (w, 8-channel group).  Kernel rows i = 0..3 read frames vf - 1 + i of the
+// zero-extended utterance; variants: 0 = all rows, 1 = rows 1..3 (window row 0), 2 = rows 0..2 (row 33), 3 = rows 0..1 (row 34).
+__global__ void __launch_bounds__(256)
+frame_conv_kernel(const FrameConvDev p) {
+  __shared__ float s_w[16 * 64];
+  __shared__ int s_u;
+  for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) s_w[i] = p.w[i];
+  const long long crow = p.crow0 + blockIdx.x;
+  if (threadIdx.x == 0) {
+    int a = p.u_first, b = p.u_last + 1;               // largest u with frame_offs[u] + 34 u <= crow
+    while (b - a > 1) {
+      const int mid = (a + b) >> 1;
+      if (p.frame_offs[mid] + 2LL * kVirt * mid <= crow) a = mid; else b = mid;
+    }
+    s_u = a;
+  }
+  __syncthreads();
+  const int u = s_u;
+  const long long f0 = p.frame_offs[u];
+  const int T = (int)(p.frame_offs[u + 1] - f0);
+  const int vf = (int)(crow - (f0 + 2LL * kVirt * u)) - kVirt;    // virtual frame of this row
+  const float* rows[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int fr = vf - 1 + i;
+    rows[i] = (fr >= 0 && fr < T) ? p.raw + (size_t)(f0 + fr) * 201 : nullptr;
+  }
+  float* out = p.C + (size_t)blockIdx.x * 201 * 64;
+  const size_t vplane = (size_t)p.crow_cap * 201 * 64;
+  for (int it = threadIdx.x; it < 201 * 16; it += blockDim.x) {
+    const int w = it >> 4, cg = (it & 15) * 4;
+    float P[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) P[i][c] = 0.f;
+      if (!rows[i]) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = w - 1 + j;
+        if (f < 0 || f >= 201) continue;
+        const float x = __ldg(rows[i] + f);
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(i * 4 + j) * 64 + cg]);
+        P[i][0] = fmaf(x, w0.x, P[i][0]); P[i][1] = fmaf(x, w0.y, P[i][1]); P[i][2] = fmaf(x, w0.z, P[i][2]); P[i][3] = fmaf(x, w0.w, P[i][3]);
+      }
+    }
+    // everything that does not depend on the window row: conditioning bias of this utterance + F[w]
+    float add[4];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + (size_t)u * p.bias_stride + cg));
+      add[0] = b0.x; add[1] = b0.y; add[2] = b0.z; add[3] = b0.w;
+      if (p.ftab16) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p.ftab16 + w * 64 + cg));
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        add[0] += f0.x; add[1] += f0.y; add[2] += f1.x; add[3] += f1.y;
+      }
+    }
+    float v[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float p01 = P[0][c] + P[1][c];
+      v[3][c] = p01 + add[c];
+      v[2][c] = (p01 + P[2][c]) + add[c];
+      v[0][c] = ((p01 + P[2][c]) + P[3][c]) + add[c];
+      v[1][c] = ((P[1][c] + P[2][c]) + P[3][c]) + add[c];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<float4*>(out + k * vplane + (size_t)w * 64 + cg) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+  }
+}
+
+// grid: (ceil(units / 8), ceil(Wo / CW)); a warp owns one window and walks its 35 rows over a CW-pixel column chunk,
+// so the 8 warps of a CTA re-read the same C rows (row h of window n is row h - 1 of window n + 1) from L1 / L2.
+template <int CW>
+__global__ void __launch_bounds__(256)
+window_expand_kernel(const DirectDev p, const float* __restrict__ C, long long crow0, long long crow_cap, int unit0, int unit1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = unit0 + blockIdx.x * 8 + warp;
+  if (unit >= unit1) return;
+  const EpiDev& e = p.epi;
+  const int cg = (lane & 7) * 8;
+  const int utt = p.units_tab.utt ? p.units_tab.utt[unit] : 0;
+  const long long crow_n = (long long)p.units_tab.frame[unit] + 2LL * kVirt * utt - crow0;   // C row of window row 0
+  const size_t vplane = (size_t)crow_cap * 201 * 64;
+  constexpr int NIT = CW / 4;
+  // per-lane pixel offsets of the column iterations (independent of the window row)
+  long long off[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int xx = blockIdx.y * CW + (lane >> 3) + 4 * it + e.o_ox;
+    off[it] = ((long long)(xx % e.o_sw) * e.o_plane + unit * e.o_ustride + (xx / e.o_sw)) * e.out_C + cg;
+  }
+  const int wo0 = blockIdx.y * CW + (lane >> 3);
+  const float* cbase = C + (size_t)crow_n * 201 * 64 + cg;
+  for (int h = 0; h < p.Ho; ++h) {
+    const int variant = h == 0 ? 1 : (h == p.Ho - 2 ? 2 : (h == p.Ho - 1 ? 3 : 0));
+    const float* crow = cbase + variant * vplane + (size_t)h * 201 * 64;
+    float bt[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (e.ttab16) add_half8(bt, __ldg(reinterpret_cast<const uint4*>(e.ttab16 + h * 64 + cg)));
+    const int yy = h + e.o_oy;
+    __half* orow = e.out + ((long long)((yy % e.o_sh) * e.o_sw) * e.o_plane + (long long)(yy / e.o_sh) * e.o_rstride) * e.out_C;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int wo = wo0 + 4 * it;
+      if (wo >= p.Wo) continue;
+      const float4* c4 = reinterpret_cast<const float4*>(crow + (size_t)wo * 64);
+      const float4 a0 = __ldg(c4), a1 = __ldg(c4 + 1);
+      float v[8] = {a0.x + bt[0], a0.y + bt[1], a0.z + bt[2], a0.w + bt[3], a1.x + bt[4], a1.y + bt[5], a1.z + bt[6], a1.w + bt[7]};
+      if (e.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      uint4 o;
+      o.x = pack_half2(v[0], v[1]); o.y = pack_half2(v[2], v[3]);
+      o.z = pack_half2(v[4], v[5]); o.w = pack_half2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(orow + off[it]) = o;
+    }
+  }
+}
+
 // bias_utt[u][j] = emb_a[u] . Pa[:, j] + emb_b[u] . Pb[:, j] + c[j]   (all 32 conditioning projections of
 // main.py:142-148 with the batch-norm scale of their site folded in; one small fp32 GEMM per batch)
 constexpr int kCondU = 8;
@@ -352,6 +476,20 @@ cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p) {
   const long long blocks = (total + threads - 1) / threads;
   const size_t smem = (size_t)p.kh * p.kw * 64 * 4 + 4 * 32 * kDirectPitch * 4 + 2 * 4 * 32 * 4 + 4 * 64 * 4;
   direct_conv64_kernel<<<(unsigned)blocks, threads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frame_conv(cudaStream_t s, const FrameConvDev& p) {
+  if (p.rows <= 0) return cudaSuccess;
+  frame_conv_kernel<<<p.rows, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_window_expand(cudaStream_t s, const DirectDev& d, const float* C, long long crow0, long long crow_cap, int unit0,
+                                 int unit1) {
+  if (unit1 <= unit0) return cudaSuccess;
+  if (d.N != 64 || d.kh != 4 || d.kw != 4 || d.sh != 1 || d.sw != 1 || d.pt != 1 || d.pl != 1 || d.Win != 201) return cudaErrorInvalidValue;
+  window_expand_kernel<8><<<dim3((unit1 - unit0 + 7) / 8, (d.Wo + 7) / 8), 256, 0, s>>>(d, C, crow0, crow_cap, unit0, unit1);
   return cudaGetLastError();
 }
 
