@@ -174,3 +174,21 @@ def test_many_tiny_utterances(engine_sn, oracle_sn):
         assert _snr(ref, res["f32"][u]) >= SNR_MIN_DB
     solo = engine_sn.enhance([mixes[123]], None, [neg])     # alone it takes the per-frame path: same result to fp16 noise
     assert _snr(solo["f32"][0], res["f32"][123]) >= 60.0
+
+
+def test_multigpu_runtime_scatter_gather(engine_sn, weights_sn):
+    """runtime.MultiGpu: one engine per device, one host thread each, ragged batch dealt by load, results gathered
+    back in input order.  Two contexts on device 0 stand in for two GPUs (the data path has no collective)."""
+    from nhans_b200.runtime import MultiGpu
+    mixes = [synth.mixture(0.25 + 0.1 * (u % 4), 70 + u) for u in range(9)]
+    negs = [synth.noise_clip(70 + u % 2) for u in range(9)]
+    mg = MultiGpu([0, 0], W.SELECTIVE_NOISE, weights_sn, win_capacity=128, row_capacity=2)
+    try:
+        got = mg.enhance(mixes, None, negs)
+    finally:
+        mg.close()
+    ref = engine_sn.enhance(mixes, None, negs)
+    assert len(got["i16"]) == 9
+    for u in range(9):
+        assert np.array_equal(got["i16"][u], ref["i16"][u])
+        assert np.array_equal(got["f32"][u], ref["f32"][u])
