@@ -4,22 +4,27 @@
 //
 // Every convolution and dense layer of N_HANS___Selective_Noise/main.py:98-242 except the two Cin = 1
 // convolutions is lowered to this form by plan.cc (a group g = the kw taps of one kernel row and one
-// 64-channel chunk).  One persistent CTA per SM; a CTA tile is (256 / BN) sub-tiles of 128 rows x BN
-// columns, i.e. always 256 fp32 accumulator columns in TMEM, double buffered (2 x 256 = all 512 columns).
+// 64-channel chunk).  Activations live in "image-row-outer" padded grids (plan.h): a tap is a constant row
+// offset, vertical padding is TMA out-of-bounds fill, and only real output rows are enumerated; tiles are
+// ordered image-row-fastest.  Persistent CTA PAIRS (cluster of 2, cta_group::2; a single-CTA instantiation
+// serves small problems); a tile is (256 / BN) sub-tiles of 256 rows (128 per CTA) x BN columns, i.e. always
+// 256 fp32 accumulator columns in TMEM, double buffered (2 x 256 = all 512 columns).
 //
 //   warp 8   A producer     one TMA box of 136 rows x 64 channels ("slab") per (group, sub-tile): the kw taps
 //                           of a kernel row read the SAME slab through UMMA descriptors whose start address
 //                           is shifted by `shift` rows, so A comes from L2 once per kernel row, not per tap
-//   warp 9   B producer     one TMA box BN x 64 per k-block into its own ring; when all k-blocks of the layer
-//                           fit (K * BN * 2 B <= ring) the weights are loaded once and stay resident
-//   warp 10  MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, 4 x (K = 16) per tap,
-//                           fp32 accumulators in TMEM
-//   warps 0-7 epilogue      tcgen05.ld (thread = row) -> shared-memory transpose (warp-private 32 x 32) ->
-//                           8 lanes per row x 4 channels, so every table load, the residual load and the
-//                           fp16 store are coalesced; all global loads of a chunk are issued before the
-//                           accumulator is awaited.  + per-utterance conditioning bias + time / frequency
-//                           embedding tables + scaled identity residual / rank-1 transform -> ReLU -> fp16
-//                           into the consumer's padded grid (or fp32 + centre frame for the head)
+//   warp 9   B producer     one TMA box (BN / 2) x 64 per k-block: each CTA of a pair loads half of B; the
+//                           transactions of both CTAs are credited to the leader's mbarrier
+//   warp 10  MMA issuer     leader CTA only: tcgen05.mma.cta_group::2.kind::f16, M = 256, N = BN, 4 x (K = 16)
+//                           per tap, two sub-tiles interleaved; tcgen05.commit...multicast releases ring
+//                           slots / publishes accumulators in both CTAs
+//   warps 0-7 epilogue      two flavours (kEpiRow): row-per-thread for BN <= 128 (thread = TMEM lane = GEMM
+//                           row, 16 channels per step, 256-bit residual loads and stores, fp16 tables and
+//                           per-channel vectors in shared memory, no staging) and transposing for BN = 256
+//                           (tcgen05.ld -> XOR-swizzled fp32 transpose -> 4 lanes per row, coalesced).
+//                           + per-utterance conditioning bias + time / frequency embedding tables + scaled
+//                           identity residual / rank-1 transform -> ReLU -> fp16 into the consumer's grid
+//                           (or fp32 + centre frame for the head)
 //
 // The epilogue is the fusion of blocks.py:104-108 (batch-norm), main.py:166,172 (conditioning adds),
 // main.py:184-186 (residual add, ReLU) folded as in SURVEY.md App. A.6.

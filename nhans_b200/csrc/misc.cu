@@ -1,5 +1,5 @@
-// CUDA-core kernels around the tensor-core GEMMs: the two Cin = 1 convolutions with the implicit
-// 35-frame window gather, the conditioning-projection table, the tower's global mean pool and the
+// CUDA-core kernels around the tensor-core GEMMs: the Cin = 1 convolutions (per-frame evaluation + window
+// expansion for the mask network, per-unit kernels with the implicit window gather for the towers / fallback), the conditioning-projection table, the tower's global mean pool and the
 // per-unit lookup tables.
 #include "kernels.h"
 
