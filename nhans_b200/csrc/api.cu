@@ -52,6 +52,8 @@ struct GemmLayerDev {
   float *bias = nullptr, *tftab = nullptr, *res_scale = nullptr, *r1_vec = nullptr;
   uint16_t *ttab16 = nullptr, *ftab16 = nullptr;
   CUtensorMap mapA0, mapA1, mapB, mapBhalf;
+  __half* w_walk = nullptr;         // row-walk layers: weights as [(3 - kh) * 64 + cout][kw * 64 + cin]
+  CUtensorMap mapBwalk;
 };
 
 struct NetDev {
@@ -112,6 +114,7 @@ struct nhans_ctx {
   int debug_skip_epilogue = 0;
   unsigned long long* debug_stats = nullptr;   // [128][8] per-layer wait-cycle counters (NHANS_DEBUG_STATS=1)
   int desc_mode = 0;
+  bool use_walk = true;             // row-walk kernel for the 64-channel stage (NHANS_NO_WALK=1: plain N = 64 GEMM)
   double layer_acc[128][4] = {};
   double launches = 0;              // every kernel launched by this context (counted even when not profiling)
 };
@@ -233,6 +236,20 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
     }
     if ((rc = make_map(ctx, &D.mapB, D.w, L.K, L.N, L.BN))) return rc;
     if ((rc = make_map(ctx, &D.mapBhalf, D.w, L.K, L.N, L.BN % 32 == 0 ? L.BN / 2 : L.BN))) return rc;   // CTA pairs load half of B each
+    if (L.walk) {
+      if (L.c_kh != 4 || L.c_kw != 4 || L.N != 64 || L.K != 16 * 64) return fail(ctx, NHANS_ERR_STATE, "row-walk layer with an unexpected shape");
+      std::vector<uint16_t> ww((size_t)256 * 256);
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw)
+          for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < 64; ++ci)
+              ww[(size_t)((3 - kh) * 64 + co) * 256 + kw * 64 + ci] = L.w[(size_t)co * L.K + (kh * 4 + kw) * 64 + ci];
+      uint16_t* dw = nullptr;
+      if ((rc = upload(ctx, net, ww, &dw))) return rc;
+      CK(cudaStreamSynchronize(ctx->stream));          // `ww` is a temporary
+      D.w_walk = reinterpret_cast<__half*>(dw);
+      if ((rc = make_map(ctx, &D.mapBwalk, D.w_walk, 256, 256, 256))) return rc;
+    }
   }
   const int cap = P.capacity;
   for (int** p : {&net.u_frame, &net.u_lo, &net.u_hi, &net.u_utt}) {
@@ -400,6 +417,17 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
     g.debug_stats = ctx->debug_stats ? ctx->debug_stats + 8 * ((&net == &ctx->tower ? 64 : 0) + (int)i) : nullptr;
     ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0, (&net == &ctx->tower ? 64 : 0) + (int)i);
+    if (L.walk && D.w_walk && ctx->use_walk) {
+      WalkDev wd;
+      memset(&wd, 0, sizeof wd);
+      wd.plane_pitch = g.plane_pitch; wd.plane_rows = g.plane_rows;
+      wd.H = L.Ho; wd.Wq = L.Wq; wd.Wo = L.Wo; wd.pt = L.c_pt; wd.pl = L.c_pl;
+      wd.units = ut; wd.epi = g.epi; wd.err_flag = g.err_flag; wd.debug_stats = g.debug_stats;
+      cudaError_t le = launch_walk(ctx->stream, ctx->n_sm, D.mapA0, D.mapBwalk, wd);
+      if (le != cudaSuccess)
+        return fail(ctx, NHANS_ERR_CUDA, "launch of row-walk layer " + L.name + ": " + cudaGetErrorString(le));
+      continue;
+    }
     {
       cudaError_t le = launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, D.mapBhalf, g, ctx->desc_mode);
       if (le != cudaSuccess)
@@ -514,6 +542,7 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   if (row_capacity > 0) ctx->row_cap = row_capacity;
   if (const char* dbg = getenv("NHANS_DEBUG_SKIP_EPILOGUE")) ctx->debug_skip_epilogue = atoi(dbg);
   if (const char* dbg = getenv("NHANS_DESC_MODE")) ctx->desc_mode = atoi(dbg);
+  if (const char* dbg = getenv("NHANS_NO_WALK")) ctx->use_walk = atoi(dbg) == 0;
   if (const char* dbg = getenv("NHANS_DEBUG_STATS")) {
     if (atoi(dbg) && cudaMalloc((void**)&ctx->debug_stats, 128 * 8 * 8) == cudaSuccess) cudaMemset(ctx->debug_stats, 0, 128 * 8 * 8);
   }

@@ -80,6 +80,18 @@ struct GemmDev {
   unsigned long long* debug_stats;   // optional [8] cycle counters (wait times per role), or null
 };
 
+// Row-walk kernel (conv_walk.cu): stride-1 4 x 4 convolution, 64 -> 64 channels, over the compute space of GemmDev.
+struct WalkDev {
+  int plane_pitch;          // capacity * Wq
+  int plane_rows;           // units * Wq
+  int H, Wq, Wo;            // image rows (in = out), row segment pitch, valid pixels per segment
+  int pt, pl;               // top / left padding
+  UnitTable units;
+  EpiDev epi;
+  int* err_flag;
+  unsigned long long* debug_stats;
+};
+
 struct DirectDev {
   int units;
   int kh, kw, sh, sw, pt, pl;
@@ -96,6 +108,8 @@ cudaError_t gemm_configure();   // sets the dynamic shared-memory attribute once
 cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, const CUtensorMap& mapA1,
                         const CUtensorMap& mapB, const CUtensorMap& mapBhalf, const GemmDev& p, int desc_mode);
 cudaError_t launch_direct_conv(cudaStream_t s, const DirectDev& p);
+// mapA: the input grid as [pixels][64] (box 136 x 64), mapB: repacked weights [4 kernel-row blocks x 64][4 x 64] (box 256 x 64)
+cudaError_t launch_walk(cudaStream_t s, int n_sm, const CUtensorMap& mapA, const CUtensorMap& mapB, const WalkDev& p);
 
 // First convolution of the mask network, computed once per FRAME instead of once per (window, row): the 35-frame
 // windows of one utterance are shifted copies of the same spectrogram, so conv(x)[window n, row h] depends only on

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -301,6 +302,13 @@ struct Builder {
     L->K = K;
   }
 
+  // Stride-1 4 x 4 convolutions with 64 channels in and out can be executed by the row-walk kernel.
+  static void mark_walk(GemmLayer* L, const BlockSpec& b, int Cin, int C, int pt, int pl) {
+    if (b.pair || b.kh != 4 || b.kw != 4 || b.sh != 1 || b.sw != 1 || Cin != 64 || C != 64) return;
+    L->walk = 1;
+    L->c_kh = b.kh; L->c_kw = b.kw; L->c_pt = pt; L->c_pl = pl;
+  }
+
   // One residual block (both flavours).  x: input grid (buf < 0 when Cin = 1: raw spectrogram).
   // y: output grid (already allocated, laid out for its consumer).
   void add_block(const BlockSpec& b, const BlockGeom& g, const Grid& x, const Grid& y, int Hin_raw, int raw_oh) {
@@ -349,6 +357,7 @@ struct Builder {
       L.epi = e1;
       L.out = h;
       L.macs_per_unit = macs1;
+      mark_walk(&L, b, Cin, C, g.pt, g.pl);
       build_groups(&L);
       plan.gemm.push_back(std::move(L));
     }
@@ -400,6 +409,7 @@ struct Builder {
     site_epilogue(b.scope + "_conv2", C, g.Ho, g.Wo, bnA.s, constant, &e2);
     L.epi = e2;
     L.out = y;
+    if (L.a_buf[1] < 0) mark_walk(&L, b, C, C, g.pt2, g.pl2);
     build_groups(&L);
     plan.gemm.push_back(std::move(L));
   }
@@ -510,9 +520,9 @@ std::string plan_to_json(const NetPlan& p) {
     char b[512];
     snprintf(b, sizeof b,
              "%s{\"name\":\"%s\",\"Hq\":%d,\"Wq\":%d,\"Ho\":%d,\"Wo\":%d,\"N\":%d,\"BN\":%d,\"K\":%d,\"a_buf\":[%d,%d],"
-             "\"res_buf\":%d,\"cond_off\":%d,\"groups\":%d,\"macs\":%.1f,\"out\":",
+             "\"res_buf\":%d,\"cond_off\":%d,\"groups\":%d,\"macs\":%.1f,\"walk\":%d,\"out\":",
              i ? "," : "", L.name.c_str(), L.Hq, L.Wq, L.Ho, L.Wo, L.N, L.BN, L.K, L.a_buf[0], L.a_buf[1], L.epi.res_buf,
-             L.epi.cond_off, (int)L.groups.size(), L.macs_per_unit);
+             L.epi.cond_off, (int)L.groups.size(), L.macs_per_unit, L.walk);
     s += b + grid_json(L.out) + "}";
   }
   s += "]}";
@@ -523,8 +533,12 @@ NetPlan build_main_plan(const WeightMap& w, int variant, int capacity) {
   Builder B(w, capacity, true);
   if (variant == 0) { B.sa = "_noise_pos_emb"; B.sb = "_noise_neg_emb"; }
   else              { B.sa = "_noise_emb";     B.sb = "_clean_emb"; }
+  // 64-channel stage: plain pixel rows executed by the row-walk kernel (default), or the pixel-pair GEMM rows of
+  // round 1 (NHANS_STAGE1=pair; kept for A/B measurements)
+  const char* s1 = getenv("NHANS_STAGE1");
+  const bool pair1 = s1 && std::string(s1) == "pair";
   std::vector<BlockSpec> blocks = {                      // main.py:221-229
-      {"resblock1_1", 4, 4, 1, 1, 64, true},  {"resblock1_2", 4, 4, 1, 1, 64, true},
+      {"resblock1_1", 4, 4, 1, 1, 64, pair1},  {"resblock1_2", 4, 4, 1, 1, 64, pair1},
       {"resblock2_1", 4, 4, 2, 2, 128}, {"resblock2_2", 4, 4, 1, 1, 128},
       {"resblock3_1", 3, 3, 2, 2, 256}, {"resblock3_2", 3, 3, 1, 1, 256},
       {"resblock4_1", 3, 3, 2, 2, 512}, {"resblock4_2", 3, 3, 1, 1, 512}};

@@ -119,6 +119,11 @@ struct GemmLayer {
   Epilogue epi;
   Grid out;                               // out.buf < 0 for the head
   double macs_per_unit = 0;               // algorithmic MACs per window / context row
+  // Row-walk eligible (conv_walk.cu): a stride-1 4 x 4 convolution with 64 channels in and out and no second A
+  // source.  The k-blocks / weights above stay valid (plain N = 64 GEMM, what the CPU interpreter executes); the
+  // engine repacks the weights as [kernel row block][cout] x [kw][cin] and walks the image rows instead.
+  int walk = 0;
+  int c_kh = 0, c_kw = 0, c_pt = 0, c_pl = 0;
 };
 
 struct DirectLayer {

@@ -82,3 +82,33 @@ def test_padding_positions_stay_zero(engine_sn):
         pix = grid_gather(g, np.arange(g["pixels"])[:, None], plan["capacity"])[..., 0]
         mask[pix.ravel()] = False
         assert not np.any(buf[mask]), g
+
+
+def test_row_walk_matches_plain_gemm(engine_sn, weights_sn, monkeypatch):
+    """The 64-channel stage runs on the row-walk kernel (conv_walk.cu); NHANS_NO_WALK=1 executes the same layers as
+    plain N = 64 shifted-row GEMMs.  Same fp16 operands, same fp32 products, other summation order: every activation
+    grid of the stage agrees to fp16 rounding noise, over several passes and a ragged last tile."""
+    from nhans_b200.engine import Engine
+    rng = np.random.default_rng(11)
+    lm = rng.normal(-3, 2, (300 + 77, 201)).astype(np.float32)         # 256 + 121 windows: 2 passes, 3 utterances
+    fo = np.array([0, 40, 300, 377])
+    ea = rng.normal(0, 1, (3, 512)).astype(np.float32)
+    eb = rng.normal(0, 1, (3, 512)).astype(np.float32)
+    assert sum(g["walk"] for g in engine_sn.plan(0)["gemm"]) == 3
+    den = engine_sn.masknet(lm, fo, ea, eb)
+    monkeypatch.setenv("NHANS_NO_WALK", "1")
+    plain = Engine(0, 0, win_capacity=256, row_capacity=4)
+    try:
+        plain.load_weights(weights_sn)
+        den_p = plain.masknet(lm, fo, ea, eb)
+        assert np.abs(den - den_p).max() < 2e-3
+        for g in engine_sn.plan(0)["gemm"]:
+            if not g["walk"]:
+                continue
+            grid = g["out"]
+            a = grid_gather(grid, engine_sn.read_buffer(0, grid["buf"]).astype(np.float32), 121)
+            b = grid_gather(grid, plain.read_buffer(0, grid["buf"]).astype(np.float32), 121)
+            assert _rel(a, b) < 2e-4, g["name"]
+            assert np.abs(a - b).max() <= 2e-3 * max(1.0, float(np.abs(b).max())), g["name"]
+    finally:
+        plain.close()
