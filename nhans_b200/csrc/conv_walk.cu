@@ -148,34 +148,43 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
       const long long j0 = seq * H;
       for (int r = 0; r < H; ++r) {
-        WalkStep st;
-        walk_step(seq, r, H, p.pt, &st);
-        for (int c = 0; c < st.n_claim; ++c) {
-          const long long J = j0 + st.claim_job[c];
+        const WalkWin w = walk_window(seq, r, H, p.pt);
+        for (int c = 0; c < w.n_fresh; ++c) {           // slots claimed by this step: wait until the epilogue has read them
+          const long long J = j0 + w.o_lo + w.n - w.n_fresh + c;
           ptx::mbar_wait_timed(&ctrl->tmem_empty[J & (kWalkSlots - 1)], (uint32_t)(((J >> 3) & 1) ^ 1), p.err_flag, 2, &w_tmem);
         }
         ptx::mbar_wait_timed(&ctrl->a_full[aslot], aphase, p.err_flag, 3, &w_a);
         ptx::tc_fence_after();
         const uint32_t a_lo = a_base + aslot * (kSlabBytes >> 4);
-#pragma unroll 1
-        for (int kk = 0; kk < kWalkKW * 4; ++kk) {
+        const uint64_t da0 = desc_hi | (uint64_t)a_lo;
+        const uint64_t db0 = desc_hi | (uint64_t)b_base;
+        // K step 0 (tap 0, k = 0): fresh slots do not accumulate
+        if (ptx::elect_one()) {
+          walk_segments(w, true, [&](int slot, int bi, int nb, int fresh) {
+            ptx::umma_f16(tmem_base + (uint32_t)slot * 64, da0, db0 + (uint64_t)(bi * ((64 * 128) >> 4)),
+                          idesc0 | ((uint32_t)(nb * 64 >> 3) << 17), fresh ? 0u : 1u);
+          });
+        }
+        __syncwarp();
+        // the other 15 K steps: one MMA over the whole window, two where the slot ring wraps
+        const uint32_t d_a = tmem_base + (uint32_t)w.slot0 * 64, d_b = tmem_base;
+        const uint32_t i_a = idesc0 | ((uint32_t)(w.n1 * 64 >> 3) << 17), i_b = idesc0 | ((uint32_t)((w.n - w.n1) * 64 >> 3) << 17);
+        const uint64_t db_a = db0 + (uint64_t)(w.bi0 * ((64 * 128) >> 4)), db_b = db_a + (uint64_t)(w.n1 * ((64 * 128) >> 4));
+        const bool two = w.n > w.n1;
+#pragma unroll
+        for (int kk = 1; kk < kWalkKW * 4; ++kk) {
           const int kw = kk >> 2, k = kk & 3;
-          const bool first = kk == 0;
-          const int nseg = first ? st.n_first : st.n_rest;
           if (ptx::elect_one()) {
-            const uint64_t da = (desc_hi | (uint64_t)(a_lo + kw * 8)) + 2 * k;          // tap kw = slab rows shifted by kw
-            const uint64_t db = (desc_hi | (uint64_t)(b_base + kw * (kBTile >> 4))) + 2 * k;
-            for (int s = 0; s < nseg; ++s) {
-              const WalkSeg sg = first ? st.first[s] : st.rest[s];
-              ptx::umma_f16(tmem_base + (uint32_t)sg.slot * 64, da, db + (uint64_t)sg.bi * ((64 * 128) >> 4),
-                            idesc0 | ((uint32_t)(sg.nb * 64 >> 3) << 17), (first && sg.fresh) ? 0u : 1u);
-            }
+            const uint64_t da = da0 + (uint64_t)(kw * 8 + 2 * k);                 // tap kw = slab rows shifted by kw
+            const uint64_t bo = (uint64_t)(kw * (kBTile >> 4) + 2 * k);
+            ptx::umma_f16(d_a, da, db_a + bo, i_a, 1u);
+            if (two) ptx::umma_f16(d_b, da, db_b + bo, i_b, 1u);
           }
           __syncwarp();
         }
         if (ptx::elect_one()) {
           ptx::umma_commit(&ctrl->a_empty[aslot]);
-          for (int d = 0; d < st.n_done; ++d) ptx::umma_commit(&ctrl->tmem_full[(j0 + st.done_job[d]) & (kWalkSlots - 1)]);
+          for (int d = 0; d < w.n_done; ++d) ptx::umma_commit(&ctrl->tmem_full[(j0 + w.done_lo + d) & (kWalkSlots - 1)]);
         }
         __syncwarp();
         if (++aslot == (uint32_t)kNA) { aslot = 0; aphase ^= 1; }

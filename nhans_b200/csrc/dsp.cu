@@ -7,11 +7,21 @@
 //   exp(logmag) e^{j phase} -> irfft-400 -> synthesis window -> 3-frame gather overlap-add ->
 //   float32 and/or int16 PCM, fused in one kernel (istft_kernel), no atomics.
 //
-// FFT-400 is not a power of two: the real transform is done as one complex FFT-200 on
-// packed even/odd samples, 200 = 8 x 25 (radix-8 butterflies, then 5 x 5), all in shared memory and
-// registers; each CTA stages the contiguous sample span of its frames once.
+// FFT-400 is not a power of two: the real transform is one complex FFT-200 on packed even/odd
+// samples, 200 = 8 x 25.  Round 2 layout (round 1 ran three block-wide passes with a __syncthreads after each and was
+// issue / latency bound at 0.2 of the HBM roofline): a WARP owns four frames from the samples to the spectrum and
+// synchronises with __syncwarp only -
+//   pass A   25 radix-8 butterflies per frame (window / pre-twiddle fused), 100 tasks over 32 lanes
+//   pass B   8 DFT-25 per frame, each entirely in the registers of one lane (two radix-5 stages, compile-time
+//            twiddles): 4 frames x 8 = exactly one task per lane, in place
+//   post     bins k and 200 - k of the real transform come from the same two DFT values: 101 pair tasks per frame,
+//            lanes walk consecutive bins so that the global stores are coalesced
+// One 1.6 KB buffer per frame is the whole working set (pass A and B run in place).  The forward kernel stages the
+// int16 span of its 16 frames with one 1-D bulk TMA copy (cp.async.bulk, mbarrier completion) and converts each
+// sample once; the inverse kernel gathers 30 output hops from 32 frames and writes 128-bit / 64-bit vectors.
 #include "kernels.h"
 #include "fft400.cuh"
+#include "ptx.cuh"
 
 #include <math.h>
 #include <vector>
@@ -23,9 +33,14 @@ namespace {
 constexpr int kWin = 400;
 constexpr int kHop = 160;
 constexpr int kBinsD = 201;
-constexpr int kFB = 10;                 // frames per CTA (forward)
-constexpr int kOH = 12;                 // output hops per CTA (inverse) -> kOH + 2 frames (2 / 12 recomputed)
-constexpr int kThreads = 256;
+constexpr int kFW = 4;                  // frames per warp
+constexpr int kSW = 4;                  // warps per CTA (forward)
+constexpr int kFB = kFW * kSW;          // frames per CTA (forward)
+constexpr int kSpanF = (kFB - 1) * kHop + kWin;
+constexpr int kIW = 8;                  // warps per CTA (inverse)
+constexpr int kNFI = kFW * kIW;         // frames per CTA (inverse)
+constexpr int kOH = kNFI - 2;           // output hops per CTA (2 of 32 frames are recomputed by the neighbour)
+constexpr int kThreads = 256;           // inverse kernels
 
 __device__ float2 g_tw200[200];         // e^{-2 pi i t / 200}
 __device__ float2 g_tw400[201];         // e^{-2 pi i k / 400}
@@ -33,24 +48,6 @@ __device__ __align__(16) float g_hann[400];           // 0.5 - 0.5 cos(2 pi n / 
 __device__ __align__(16) float g_winv[400];           // hann[n] / sum_j hann^2[n mod 160 + 160 j]
 
 using namespace fft;
-
-__device__ float2 g_tw25[25];            // e^{-2 pi i t / 25} (thread-dependent index: not __constant__)
-
-// Complex DFT-200 of nf frames held in shared memory: a -> b -> a -> b (three passes, a sync after each).
-template <bool INV>
-__device__ __forceinline__ void fft200_tail(float2* __restrict__ a, float2* __restrict__ b, int nf) {
-  // pass B1 / B2 after the caller's pass A left its result in `a`
-  for (int t = threadIdx.x; t < nf * 40; t += blockDim.x) {
-    const int f = t / 40, r = t - f * 40;
-    fft200_step_b1<INV>(a, b, f, r / 5, r % 5, g_tw25);
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < nf * 40; t += blockDim.x) {
-    const int f = t / 40, r = t - f * 40;
-    fft200_step_b2<INV>(b, a, f, r & 7, r >> 3);
-  }
-  __syncthreads();
-}
 
 // numpy: abs(int16(-32768)) == -32768, so that sample never wins the max (SN/apply.py:150)
 __device__ __forceinline__ int abs16(int v) { return v == -32768 ? -32768 : (v < 0 ? -v : v); }
@@ -71,17 +68,54 @@ __global__ void peak_kernel(const int16_t* __restrict__ pcm, const long long* __
   }
 }
 
-// grid: (ceil(max_frames / kFB), U).  PHASOR: the second output is the unit phasor X / |X| as float2 ((1, 0) where
-// X = 0) instead of the angle - what the fused path keeps between the two transforms (no atan2 here,
-// no sincos in the inverse).  Windowing is fused into the first butterfly pass (every sample is used once there).
+// One spectrum value -> log-magnitude and phase (or unit phasor) of bin `o`.
 template <bool PHASOR>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void emit_bin(float re, float im, size_t o, float* __restrict__ logmag, float* __restrict__ phase) {
+  const float r2 = re * re + im * im;
+  if (PHASOR) {
+    const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
+    logmag[o] = __logf(r2 * inv + 1e-5f);
+    reinterpret_cast<float2*>(phase)[o] = r2 > 0.f ? make_float2(re * inv, im * inv) : make_float2(1.f, 0.f);
+  } else {
+    logmag[o] = __logf(sqrtf(r2) + 1e-5f);
+    if (phase) phase[o] = atan2f(im, re);
+  }
+}
+
+// Pass B of the DFT-200 for the (up to) four frames of a warp, in place: lane = (frame, k1) owns one DFT-25.
+template <bool INV>
+__device__ __forceinline__ void warp_pass_b(float2* __restrict__ z, int nfw, int lane) {
+  const int f = lane >> 3, k1 = lane & 7;
+  float2 y[25];
+  if (f < nfw) {
+    const float2* src = z + f * 200 + k1 * 25;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) y[i] = src[i];
+    dft25<INV>(y);
+  }
+  __syncwarp();                         // every lane has read its inputs before anyone overwrites them
+  if (f < nfw) {
+    float2* dst = z + f * 200 + k1;
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+      for (int d = 0; d < 5; ++d) dst[8 * (c + 5 * d)] = y[5 * c + d];
+  }
+  __syncwarp();
+}
+
+// grid: (ceil(max_frames / kFB), U), 128 threads.  PHASOR: the second output is the unit phasor X / |X| as float2
+// ((1, 0) where X = 0) instead of the angle - what the fused path keeps between the two transforms (SURVEY.md A.3:
+// no atan2 here, no sincos in the inverse).
+template <bool PHASOR>
+__global__ void __launch_bounds__(kSW * 32)
 stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const long long* __restrict__ offs,
             const long long* __restrict__ frame_offs, const int* __restrict__ peak, float* __restrict__ logmag,
             float* __restrict__ phase) {
-  __shared__ __align__(16) float s_x[(kFB - 1) * kHop + kWin];
-  __shared__ float2 s_a[kFB * 200];
-  __shared__ float2 s_b[kFB * 200];
+  __shared__ __align__(16) int16_t s_raw[kSpanF + 16];        // TMA landing zone: 16-byte aligned start and size
+  __shared__ __align__(16) float s_x[kSpanF];
+  __shared__ __align__(16) float2 s_z[kSW][kFW * 200];
+  __shared__ __align__(8) uint64_t s_bar;
   const int u = blockIdx.y;
   const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
   const int t0 = blockIdx.x * kFB;
@@ -92,45 +126,63 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
   if (xf) {                              // already-normalised float samples (apply_demo, SN/apply.py:241-247)
     for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = xf[base + i];
   } else {
+    // one bulk copy of the int16 span, from the 16-byte boundary below its first sample
+    const long long abase = base & ~7LL;
+    const int shift = (int)(base - abase);
+    const uint32_t bytes = (uint32_t)(((shift + span) * 2 + 15) & ~15);
+    if (threadIdx.x == 0) {
+      ptx::mbar_init(&s_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ptx::mbar_expect_tx(&s_bar, bytes);
+      ptx::bulk_load_1d(s_raw, pcm + abase, bytes, &s_bar);
+    }
+    while (!ptx::mbar_try_wait(&s_bar, 0)) {}
     // x / (peak + 1e-6) in float64 like the reference, as a multiplication by the float64 reciprocal (differs from
     // the true quotient by < 1 float64 ulp before the rounding to float32; nhans_normalise keeps the exact division)
     const double inv = 1.0 / ((double)peak[u] + 0.000001);
-    for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)pcm[base + i] * inv);
+    for (int i = threadIdx.x; i < span; i += blockDim.x) s_x[i] = (float)((double)s_raw[shift + i] * inv);
   }
   __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nfw = min(kFW, nf - warp * kFW);          // frames of this warp
+  if (nfw <= 0) return;
+  float2* z = s_z[warp];
+  const float* x0 = s_x + warp * kFW * kHop;
   // pass A on the windowed, even/odd-packed samples z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 25 m1 + m2
-  for (int t = threadIdx.x; t < nf * 25; t += blockDim.x) {
+  for (int t = lane; t < nfw * 25; t += 32) {
     const int f = t / 25, m2 = t - f * 25;
     float2 v[8];
 #pragma unroll
     for (int m1 = 0; m1 < 8; ++m1) {
       const int m = 25 * m1 + m2;
-      const float2 xx = *reinterpret_cast<const float2*>(&s_x[f * kHop + 2 * m]);
+      const float2 xx = *reinterpret_cast<const float2*>(&x0[f * kHop + 2 * m]);
       const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + m);
       v[m1] = make_float2(xx.x * h.x, xx.y * h.y);
     }
     dft8<false>(v);
+    z[f * 200 + m2] = v[0];
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) s_a[f * 200 + k1 * 25 + m2] = cmul(v[k1], __ldg(&g_tw200[m2 * k1]));
+    for (int k1 = 1; k1 < 8; ++k1) z[f * 200 + k1 * 25 + m2] = cmul(v[k1], __ldg(&g_tw200[m2 * k1]));
   }
-  __syncthreads();
-  fft200_tail<false>(s_a, s_b, nf);
-  // X[k] = (Z[k] + conj Z[200-k]) / 2 - (i/2) e^{-2 pi i k / 400} (Z[k] - conj Z[200-k]),  k = 0..200
-  const long long row0 = frame_offs[u] + t0;
-  for (int i = threadIdx.x; i < nf * kBinsD; i += blockDim.x) {
-    const int f = i / kBinsD, k = i - f * kBinsD;
-    const float2 X = rfft_post(s_a + f * 200, k, g_tw400);
-    const float re = X.x, im = X.y;
-    const size_t o = (size_t)(row0 + f) * kBinsD + k;
-    if (PHASOR) {
-      const float r2 = re * re + im * im;
-      const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
-      logmag[o] = __logf(r2 * inv + 1e-5f);
-      reinterpret_cast<float2*>(phase)[o] = r2 > 0.f ? make_float2(re * inv, im * inv) : make_float2(1.f, 0.f);
-    } else {
-      logmag[o] = __logf(sqrtf(re * re + im * im) + 1e-5f);
-      if (phase) phase[o] = atan2f(im, re);
-    }
+  __syncwarp();
+  warp_pass_b<false>(z, nfw, lane);
+  // bins k and 200 - k from Z[k], Z[200 - k]:  with E = (Z[k] + conj Z[200-k]) / 2, P = e^{-2 pi i k / 400} (Z[k] - conj Z[200-k]) / 2:
+  //   X[k] = E - i P,   X[200 - k] = conj(E) - i conj(P)
+  const long long row0 = frame_offs[u] + t0 + warp * kFW;
+  for (int i = lane; i < nfw * 101; i += 32) {
+    const int f = i / 101, k = i - f * 101;
+    const float2 a = z[f * 200 + k];
+    const float2 b = z[f * 200 + (k ? 200 - k : 0)];
+    const float2 w = __ldg(&g_tw400[k]);
+    const float ex = 0.5f * (a.x + b.x), ey = 0.5f * (a.y - b.y);
+    const float ox = 0.5f * (a.x - b.x), oy = 0.5f * (a.y + b.y);
+    const float px = w.x * ox - w.y * oy, py = w.x * oy + w.y * ox;
+    const size_t o = (size_t)(row0 + f) * kBinsD;
+    emit_bin<PHASOR>(ex + py, ey - px, o + k, logmag, phase);
+    if (k != 100) emit_bin<PHASOR>(ex - py, -ey - px, o + 200 - k, logmag, phase);
   }
 }
 
@@ -144,98 +196,111 @@ __global__ void normalise_kernel(const int16_t* __restrict__ pcm, const long lon
     out[out_offs[u] + i] = (float)((double)pcm[offs[u] + i] / denom);
 }
 
-// Shared-memory working set of one inverse-STFT block (kOH output hops from kOH + 2 frames).
-struct IstftSmem {
-  float2 s[(kOH + 2) * kBinsD];           // spectrum, then FFT scratch, then the time-domain frames
-  float2 a[(kOH + 2) * 200];
-};
-
-// exp(logmag) e^{j phase} -> irfft-400 -> synthesis window for frames fa .. fa + kOH + 1 of clip rows
-// [row0, row0 + T); leaves the windowed frames in sm.s viewed as float [kOH + 2][400].
-// PHASOR: `phase` holds unit phasors (float2) instead of angles.
+// exp(logmag) e^{j phase} -> irfft-400 -> synthesis window for frames fa .. fa + kNFI - 1 of clip rows
+// [row0, row0 + T); leaves the windowed frames in s_y[kNFI][400] (frames outside the clip are zero).
+// PHASOR: `phase` holds unit phasors (float2) instead of angles.  Every warp transforms its own four frames;
+// the block synchronises once at the end (and once at the start: the buffer may still be read by the caller).
 template <bool PHASOR>
-__device__ __forceinline__ float* istft_frames(IstftSmem& sm, const float* __restrict__ logmag,
-                                               const float* __restrict__ phase, long long row0, int T, int fa) {
-  constexpr int NF = kOH + 2;
-  __syncthreads();                         // previous use of the buffers is over
-  for (int i = threadIdx.x; i < NF * kBinsD; i += blockDim.x) {
-    const int f = i / kBinsD, k = i - f * kBinsD;
-    const int t = fa + f;
-    float2 v = make_float2(0.f, 0.f);
+__device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const float* __restrict__ logmag,
+                                             const float* __restrict__ phase, long long row0, int T, int fa) {
+  __syncthreads();                         // previous use of the buffer is over
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* z = reinterpret_cast<float2*>(s_y) + warp * kFW * 200;
+  const int t_first = fa + warp * kFW;
+  // S[k] = exp(logmag) * phasor; Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]) and
+  // Z[200 - k] from the same pair
+  for (int i = lane; i < kFW * 101; i += 32) {
+    const int f = i / 101, k = i - f * 101;
+    const int t = t_first + f;
+    float2 sk = make_float2(0.f, 0.f), sm = sk;
     if (t >= 0 && t < T) {
-      const size_t o = (size_t)(row0 + t) * kBinsD + k;
-      const float a = expf(logmag[o]);
+      const size_t o = (size_t)(row0 + t) * kBinsD;
+      const float ak = expf(logmag[o + k]), am = expf(logmag[o + 200 - k]);
       if (PHASOR) {
-        const float2 ph = reinterpret_cast<const float2*>(phase)[o];
-        v = make_float2(a * ph.x, a * ph.y);
+        const float2 pk = reinterpret_cast<const float2*>(phase)[o + k], pm = reinterpret_cast<const float2*>(phase)[o + 200 - k];
+        sk = make_float2(ak * pk.x, ak * pk.y);
+        sm = make_float2(am * pm.x, am * pm.y);
       } else {
         float sn, cs;
-        sincosf(phase[o], &sn, &cs);
-        v = make_float2(a * cs, a * sn);
+        sincosf(phase[o + k], &sn, &cs);
+        sk = make_float2(ak * cs, ak * sn);
+        sincosf(phase[o + 200 - k], &sn, &cs);
+        sm = make_float2(am * cs, am * sn);
       }
-      if (k == 0 || k == 200) v.y = 0.f;  // irfft ignores the imaginary part of DC / Nyquist
+      if (k == 0) { sk.y = 0.f; sm.y = 0.f; }           // irfft ignores the imaginary part of DC / Nyquist
     }
-    sm.s[i] = v;
+    const float2 w = __ldg(&g_tw400[k]);                 // conj(w) = e^{+2 pi i k / 400}
+    const float ex = sk.x + sm.x, ey = sk.y - sm.y, dx = sk.x - sm.x, dy = sk.y + sm.y;
+    const float wx = w.x * dx + w.y * dy, wy = w.x * dy - w.y * dx;          // conj(w) * d
+    z[f * 200 + k] = make_float2(ex - wy, ey + wx);
+    if (k > 0 && k < 100) z[f * 200 + 200 - k] = make_float2(ex + wy, wx - ey);
   }
-  __syncthreads();
-  // Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]), fused into butterfly pass A
-  for (int t = threadIdx.x; t < NF * 25; t += blockDim.x) {
+  __syncwarp();
+  // pass A in place: task (f, m2) reads and writes the slots 25 j + m2
+  for (int t = lane; t < kFW * 25; t += 32) {
     const int f = t / 25, m2 = t - f * 25;
     float2 v[8];
 #pragma unroll
-    for (int m1 = 0; m1 < 8; ++m1) v[m1] = irfft_pre(sm.s + f * kBinsD, 25 * m1 + m2, g_tw400);
+    for (int m1 = 0; m1 < 8; ++m1) v[m1] = z[f * 200 + 25 * m1 + m2];
     dft8<true>(v);
+    z[f * 200 + m2] = v[0];
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) sm.a[f * 200 + k1 * 25 + m2] = cmul(v[k1], cconj(__ldg(&g_tw200[m2 * k1])));
+    for (int k1 = 1; k1 < 8; ++k1) z[f * 200 + k1 * 25 + m2] = cmul(v[k1], cconj(__ldg(&g_tw200[m2 * k1])));
   }
-  __syncthreads();
-  fft200_tail<true>(sm.a, sm.s, NF);
+  __syncwarp();
+  warp_pass_b<true>(z, kFW, lane);
   // frames: y_f[2m] = Re z[m] / 400, y_f[2m+1] = Im z[m] / 400, times the synthesis window
-  float* s_y = reinterpret_cast<float*>(sm.s);          // [NF][400]
-  for (int i = threadIdx.x; i < NF * 200; i += blockDim.x) {
+  for (int i = lane; i < kFW * 200; i += 32) {
     const int f = i / 200, m = i - f * 200;
-    const float2 z = sm.a[i];
+    const float2 v = z[i];
     const float2 w = __ldg(reinterpret_cast<const float2*>(g_winv) + m);
-    *reinterpret_cast<float2*>(&s_y[f * kWin + 2 * m]) = make_float2(z.x * (1.0f / 400.0f) * w.x, z.y * (1.0f / 400.0f) * w.y);
+    z[i] = make_float2(v.x * (1.0f / 400.0f) * w.x, v.y * (1.0f / 400.0f) * w.y);
   }
   __syncthreads();
-  return s_y;
 }
 
-// 3-frame gather overlap-add of sample i of the block (local hop hl = i / 160)
-__device__ __forceinline__ float ola_sample(const float* s_y, int i) {
+// 3-frame gather overlap-add of samples i .. i + 3 of the block (i % 4 == 0, so all four lie in hop hl = i / 160)
+__device__ __forceinline__ float4 ola_sample4(const float* s_y, int i) {
   const int hl = i / kHop, r = i - hl * kHop;
   // frame local index f = hl + 2 - j covers sample offset r + 160 j, j = 0..2 (zero frames outside [0, T))
-  float acc = s_y[(hl + 2) * kWin + r] + s_y[(hl + 1) * kWin + r + kHop];
-  if (r + 2 * kHop < kWin) acc += s_y[hl * kWin + r + 2 * kHop];
+  const float4 a = *reinterpret_cast<const float4*>(&s_y[(hl + 2) * kWin + r]);
+  const float4 b = *reinterpret_cast<const float4*>(&s_y[(hl + 1) * kWin + r + kHop]);
+  float4 acc = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  if (r + 2 * kHop < kWin) {
+    const float4 c = *reinterpret_cast<const float4*>(&s_y[hl * kWin + r + 2 * kHop]);
+    acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+  }
   return acc;
 }
 
-// grid: (ceil((max_frames + 2) / kOH), U).  Output hop h (160 samples) sums frames h-2, h-1, h.
+__device__ __forceinline__ int16_t to_i16(float v) { return (int16_t)__float2int_rn(fminf(fmaxf(v, -32768.f), 32767.f)); }
+
+// grid: (ceil((max_frames + 2) / kOH), U).  Output hop h (160 samples) sums frames h-2, h-1, h.  Clip lengths and
+// hop starts are multiples of 80 samples, so groups of four samples are aligned for 128-bit (f32) / 64-bit (int16) stores.
 template <bool PHASOR>
 __global__ void __launch_bounds__(kThreads)
 istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, const long long* __restrict__ frame_offs,
              const long long* __restrict__ out_offs, const int* __restrict__ peak, float* __restrict__ out_f32,
              int16_t* __restrict__ out_i16) {
-  __shared__ IstftSmem sm;
+  __shared__ __align__(16) float s_y[kNFI * kWin];
   const int u = blockIdx.y;
   const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
   if (T <= 0) return;
   const int h0 = blockIdx.x * kOH;        // first output hop
   if (h0 >= T + 2) return;
-  const float* s_y = istft_frames<PHASOR>(sm, logmag, phase, frame_offs[u], T, h0 - 2);
+  istft_frames<PHASOR>(s_y, logmag, phase, frame_offs[u], T, h0 - 2);
   const long long n_out = out_offs[u + 1] - out_offs[u];   // (T - 1) * 160 + 400
   const float scale = (float)((double)peak[u] + 0.000001);
-  for (int i = threadIdx.x; i < kOH * kHop; i += blockDim.x) {
+  for (int i = threadIdx.x * 4; i < kOH * kHop; i += blockDim.x * 4) {
     const long long n = (long long)h0 * kHop + i;
-    if (n >= n_out) continue;
-    const float acc = ola_sample(s_y, i);
+    if (n >= n_out) break;
+    const float4 acc = ola_sample4(s_y, i);
     const long long o = out_offs[u] + n;
-    if (out_f32) out_f32[o] = acc;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = acc;
     if (out_i16) {
-      float v = acc * scale;
-      v = fminf(fmaxf(v, -32768.f), 32767.f);
-      out_i16[o] = (int16_t)__float2int_rn(v);
+      short4 q;
+      q.x = to_i16(acc.x * scale); q.y = to_i16(acc.y * scale); q.z = to_i16(acc.z * scale); q.w = to_i16(acc.w * scale);
+      *reinterpret_cast<short4*>(out_i16 + o) = q;
     }
   }
 }
@@ -249,37 +314,38 @@ istft_post_kernel(const float* __restrict__ den_logmag, const float* __restrict_
                   const long long* __restrict__ frame_offs, const long long* __restrict__ out_offs,
                   float* __restrict__ den_f32, float* __restrict__ mixed_f32, float* __restrict__ removed_f32,
                   double* __restrict__ sums /* [U][2] */) {
-  __shared__ IstftSmem sm;
+  __shared__ __align__(16) float s_y[kNFI * kWin];
   __shared__ float s_red[2][kThreads / 32];
   const int u = blockIdx.y;
   const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
   if (T <= 0) return;
   const int h0 = blockIdx.x * kOH;
   if (h0 >= T + 2) return;
-  constexpr int PER = (kOH * kHop + kThreads - 1) / kThreads;
-  float den[PER];
-  const float* s_y = istft_frames<PHASOR>(sm, den_logmag, phase, frame_offs[u], T, h0 - 2);
+  constexpr int PER = (kOH * kHop / 4 + kThreads - 1) / kThreads;
+  float4 den[PER];
+  istft_frames<PHASOR>(s_y, den_logmag, phase, frame_offs[u], T, h0 - 2);
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
-    const int i = threadIdx.x + k * kThreads;
-    den[k] = i < kOH * kHop ? ola_sample(s_y, i) : 0.f;
+    const int i = (threadIdx.x + k * kThreads) * 4;
+    den[k] = i < kOH * kHop ? ola_sample4(s_y, i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  s_y = istft_frames<PHASOR>(sm, mix_logmag, phase, frame_offs[u], T, h0 - 2);
+  istft_frames<PHASOR>(s_y, mix_logmag, phase, frame_offs[u], T, h0 - 2);
   const long long n_out = out_offs[u + 1] - out_offs[u];
   float e_den = 0.f, e_rem = 0.f;
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
-    const int i = threadIdx.x + k * kThreads;
+    const int i = (threadIdx.x + k * kThreads) * 4;
     const long long n = (long long)h0 * kHop + i;
     if (i >= kOH * kHop || n >= n_out) continue;
-    const float mixed = ola_sample(s_y, i);
-    const float rem = mixed - den[k];                   // SN/apply.py:460
+    const float4 mixed = ola_sample4(s_y, i);
+    const float4 d = den[k];
+    const float4 rem = make_float4(mixed.x - d.x, mixed.y - d.y, mixed.z - d.z, mixed.w - d.w);     // SN/apply.py:460
     const long long o = out_offs[u] + n;
-    if (den_f32) den_f32[o] = den[k];
-    if (mixed_f32) mixed_f32[o] = mixed;
-    if (removed_f32) removed_f32[o] = rem;
-    e_den += den[k] * den[k];
-    e_rem += rem * rem;
+    if (den_f32) *reinterpret_cast<float4*>(den_f32 + o) = d;
+    if (mixed_f32) *reinterpret_cast<float4*>(mixed_f32 + o) = mixed;
+    if (removed_f32) *reinterpret_cast<float4*>(removed_f32 + o) = rem;
+    e_den += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+    e_rem += rem.x * rem.x + rem.y * rem.y + rem.z * rem.z + rem.w * rem.w;
   }
   for (int o = 16; o; o >>= 1) {
     e_den += __shfl_xor_sync(0xffffffffu, e_den, o);
@@ -336,11 +402,10 @@ cudaError_t launch_eval_loss(cudaStream_t s, const float* den, const float* tgt,
 
 cudaError_t dsp_init_tables() {
   const double kPi = 3.14159265358979323846;
-  std::vector<float2> t200(200), t400(201), t25(25);
+  std::vector<float2> t200(200), t400(201);
   std::vector<float> hann(400), winv(400);
   for (int i = 0; i < 200; ++i) t200[i] = make_float2((float)cos(2 * kPi * i / 200), (float)-sin(2 * kPi * i / 200));
   for (int i = 0; i < 201; ++i) t400[i] = make_float2((float)cos(2 * kPi * i / 400), (float)-sin(2 * kPi * i / 400));
-  for (int i = 0; i < 25; ++i) t25[i] = make_float2((float)cos(2 * kPi * i / 25), (float)-sin(2 * kPi * i / 25));
   for (int i = 0; i < 400; ++i) hann[i] = (float)(0.5 - 0.5 * cos(2 * kPi * i / 400));
   for (int i = 0; i < 400; ++i) {
     double d = 0;
@@ -353,7 +418,6 @@ cudaError_t dsp_init_tables() {
   cudaError_t e;
   if ((e = cudaMemcpyToSymbol(g_tw200, t200.data(), sizeof(float2) * 200)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_tw400, t400.data(), sizeof(float2) * 201)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyToSymbol(g_tw25, t25.data(), sizeof(float2) * 25)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_hann, hann.data(), sizeof(float) * 400)) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_winv, winv.data(), sizeof(float) * 400)) != cudaSuccess) return e;
   return cudaSuccess;
@@ -371,8 +435,8 @@ cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* off
   (void)total_frames;
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
-  if (phasor) stft_kernel<true><<<grid, kThreads, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
-  else stft_kernel<false><<<grid, kThreads, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
+  if (phasor) stft_kernel<true><<<grid, kSW * 32, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
+  else stft_kernel<false><<<grid, kSW * 32, 0, s>>>(pcm, nullptr, offs, frame_offs, peak, logmag, phase);
   return cudaGetLastError();
 }
 
@@ -380,7 +444,7 @@ cudaError_t launch_stft_f32(cudaStream_t s, const float* x, const long long* off
                             int max_frames_per_clip, float* logmag, float* phase) {
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
-  stft_kernel<false><<<grid, kThreads, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
+  stft_kernel<false><<<grid, kSW * 32, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
   return cudaGetLastError();
 }
 
@@ -398,8 +462,8 @@ cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase
   (void)total_blocks_hint;
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + 2 + kOH - 1) / kOH, U);
-  if (phasor) istft_kernel<true><<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
-  else istft_kernel<false><<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  if (phasor) istft_kernel<true><<<grid, kSW * 32, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  else istft_kernel<false><<<grid, kSW * 32, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
   return cudaGetLastError();
 }
 

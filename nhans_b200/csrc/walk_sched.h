@@ -9,14 +9,17 @@
 // issues MMAs over a sliding window of up to KH consecutive jobs; the window is cut into segments where the
 // ring wraps, at the image edges (rows outside [0, H) get no MMA at all) and - for the first K step only -
 // where freshly claimed slots (accumulate = 0) meet slots that already hold partial sums.
+//
+// Everything is closed-form arithmetic on a handful of integers (no arrays): the issuer thread keeps the whole
+// step in registers.
 #pragma once
 
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define NHANS_HD __host__ __device__ __forceinline__
+#define NHANS_WALK_HD __host__ __device__ __forceinline__
 #else
-#define NHANS_HD inline
+#define NHANS_WALK_HD inline
 #endif
 
 namespace nhans {
@@ -26,56 +29,59 @@ constexpr int kWalkKH = 4;             // kernel rows (resblock1_x: 4 x 4, main.
 constexpr int kWalkKW = 4;
 constexpr int kWalkC = 64;             // channels in = channels out
 
-struct WalkSeg {
-  int slot;                            // first ring slot (accumulator column = 64 * slot)
-  int bi;                              // first B block
-  int nb;                              // blocks: N = 64 * nb
-  int fresh;                           // 1: the slots are claimed by this step (first MMA must not accumulate)
+struct WalkWin {
+  int o_lo;                            // first output row of the window
+  int n;                               // rows in the window (1 .. KH)
+  int slot0;                           // ring slot of o_lo
+  int bi0;                             // weight block of o_lo
+  int n1;                              // rows before the ring wraps (== n when it does not)
+  int n_fresh;                         // the LAST n_fresh rows of the window are claimed by this step
+  int done_lo, n_done;                 // output rows complete after this step: [done_lo, done_lo + n_done)
 };
 
-struct WalkStep {
-  int n_first, n_rest;                 // segment counts of the first K step / of every other K step
-  WalkSeg first[4], rest[2];
-  int n_claim;                         // jobs whose slot is claimed by this step (wait until the epilogue freed it)
-  int claim_job[kWalkKH];
-  int n_done;                          // jobs complete after this step (publish to the epilogue)
-  int done_job[kWalkKH];
-};
-
-// Step for input row r of the tile with per-CTA sequence number seq; pt = rows of top padding.
-NHANS_HD void walk_step(long long seq, int r, int H, int pt, WalkStep* s) {
+// Window of input row r of the tile with per-CTA sequence number seq; pt = rows of top padding.
+NHANS_WALK_HD WalkWin walk_window(long long seq, int r, int H, int pt) {
+  WalkWin w;
   const int span = kWalkKH - 1 - pt;   // output rows above r that still receive input row r
-  int o_lo = r - span, o_hi = r + pt;
-  int bi0 = 0;
-  if (o_lo < 0) { bi0 = -o_lo; o_lo = 0; }
-  if (o_hi > H - 1) o_hi = H - 1;
+  const int lo = r - span;
+  w.o_lo = lo > 0 ? lo : 0;
+  w.bi0 = w.o_lo - lo;
+  const int o_hi = r + pt < H - 1 ? r + pt : H - 1;
+  w.n = o_hi - w.o_lo + 1;
+  w.slot0 = (int)((seq * H + w.o_lo) & (kWalkSlots - 1));
+  const int room = kWalkSlots - w.slot0;
+  w.n1 = w.n < room ? w.n : room;
   // output row o is first touched by input row max(o - pt, 0)
-  const int fresh_lo = (r == 0) ? 0 : r + pt;          // rows >= fresh_lo are claimed now
-  s->n_first = s->n_rest = s->n_claim = s->n_done = 0;
-  const long long j0 = seq * H;
-  for (int o = o_lo; o <= o_hi; ++o) {
-    const long long J = j0 + o;
-    const int slot = (int)(J % kWalkSlots);
-    const int fresh = o >= fresh_lo ? 1 : 0;
-    const int bi = bi0 + (o - o_lo);
-    if (fresh) s->claim_job[s->n_claim++] = o;
-    const bool wrap = (o != o_lo) && slot == 0;
-    if (o == o_lo || wrap) {
-      s->rest[s->n_rest++] = WalkSeg{slot, bi, 1, 0};
-    } else {
-      s->rest[s->n_rest - 1].nb++;
-    }
-    if (o == o_lo || wrap || s->first[s->n_first - 1].fresh != fresh) {
-      s->first[s->n_first++] = WalkSeg{slot, bi, 1, fresh};
-    } else {
-      s->first[s->n_first - 1].nb++;
-    }
-  }
+  int fresh_lo = (r == 0) ? 0 : r + pt;
+  if (fresh_lo < w.o_lo) fresh_lo = w.o_lo;
+  w.n_fresh = o_hi >= fresh_lo ? o_hi - fresh_lo + 1 : 0;
   // output row o is complete once input row min(o + span, H - 1) has been issued
   if (r < H - 1) {
-    if (r - span >= 0) s->done_job[s->n_done++] = r - span;
+    w.done_lo = lo;
+    w.n_done = lo >= 0 ? 1 : 0;
   } else {
-    for (int o = (r - span > 0 ? r - span : 0); o <= H - 1; ++o) s->done_job[s->n_done++] = o;
+    w.done_lo = w.o_lo;
+    w.n_done = H - w.o_lo;
+  }
+  return w;
+}
+
+// Calls f(slot, bi, nb, fresh) for every MMA of one K step: `first` = the step's first K step (fresh slots
+// must not accumulate and are therefore issued apart from the ones that hold partial sums).
+template <class F>
+NHANS_WALK_HD void walk_segments(const WalkWin& w, bool first, F&& f) {
+  auto part = [&](int a, int b, int fresh) {          // window rows [a, b), cut where the ring wraps
+    const int m = b < w.n1 ? b : w.n1;
+    if (m > a) f(w.slot0 + a, w.bi0 + a, m - a, fresh);
+    const int s = a > w.n1 ? a : w.n1;
+    if (b > s) f(w.slot0 + s - kWalkSlots, w.bi0 + s, b - s, fresh);
+  };
+  if (first) {
+    const int n_old = w.n - w.n_fresh;
+    part(0, n_old, 0);
+    part(n_old, w.n, 1);
+  } else {
+    part(0, w.n, 0);
   }
 }
 

@@ -29,45 +29,51 @@ struct Slot {
   std::set<std::pair<int, int>> terms;     // (input row, kernel row)
 };
 
-static void apply(const WalkSeg* segs, int n, bool first, long long seq, int r, int H, int pt, std::vector<Slot>& ring,
-                  std::set<std::pair<int, int>>* covered) {
-  for (int i = 0; i < n; ++i) {
-    const WalkSeg& sg = segs[i];
-    CHECK(sg.nb >= 1 && sg.slot >= 0 && sg.slot + sg.nb <= kWalkSlots, "segment leaves the ring: slot %d nb %d", sg.slot, sg.nb);
-    CHECK(sg.bi >= 0 && sg.bi + sg.nb <= kWalkKH, "segment leaves the weight blocks");
-    for (int b = 0; b < sg.nb; ++b) {
-      const int kh = kWalkKH - 1 - (sg.bi + b);
+struct Model {
+  std::vector<Slot> ring = std::vector<Slot>(kWalkSlots);
+  long long seq;
+  int r, H, pt;
+  std::set<std::pair<int, int>> covered;
+
+  void mma(int slot, int bi, int nb, int fresh, bool first) {
+    CHECK(nb >= 1 && slot >= 0 && slot + nb <= kWalkSlots, "segment leaves the ring: slot %d nb %d", slot, nb);
+    CHECK(bi >= 0 && bi + nb <= kWalkKH, "segment leaves the weight blocks");
+    for (int b = 0; b < nb; ++b) {
+      const int kh = kWalkKH - 1 - (bi + b);
       const int o = r - kh + pt;
       CHECK(o >= 0 && o < H, "product for output row %d outside the image (r %d kh %d)", o, r, kh);
-      Slot& s = ring[sg.slot + b];
-      CHECK(s.job == seq * H + o, "slot %d holds job %lld, expected %lld", sg.slot + b, s.job, seq * H + o);
+      Slot& s = ring[slot + b];
+      CHECK(s.job == seq * H + o, "slot %d holds job %lld, expected %lld", slot + b, s.job, seq * H + o);
       CHECK(!s.published, "MMA into a published slot");
       if (first) {
-        if (sg.fresh) CHECK(s.terms.empty(), "fresh slot already has terms");
+        if (fresh) CHECK(s.terms.empty(), "fresh slot already has terms");
         else CHECK(!s.terms.empty(), "accumulating into a slot that holds nothing");
-        CHECK(covered->insert({sg.slot + b, sg.bi + b}).second, "block issued twice in one K step");
+        CHECK(covered.insert({slot + b, bi + b}).second, "block issued twice in one K step");
         s.terms.insert({r, kh});
       } else {
+        CHECK(!fresh, "only the first K step may skip the accumulate");
         CHECK(s.terms.count({r, kh}) == 1, "rest list covers a block the first list did not");
-        CHECK(covered->erase({sg.slot + b, sg.bi + b}) == 1, "rest list / first list mismatch");
+        CHECK(covered.erase({slot + b, bi + b}) == 1, "rest list / first list mismatch");
       }
     }
   }
-}
+};
 
 int main() {
   long long steps = 0, mmas_first = 0, mmas_rest = 0;
   for (int pt = 0; pt <= 2; ++pt)
     for (int H : {1, 2, 3, 4, 5, 7, 8, 9, 16, 35, 37}) {
-      std::vector<Slot> ring(kWalkSlots);
+      Model M;
+      std::vector<Slot>& ring = M.ring;
+      M.H = H; M.pt = pt;
       long long published_upto = -1;          // the epilogue drains jobs in order
       for (long long seq = 0; seq < 9; ++seq) {
         for (int r = 0; r < H; ++r) {
-          WalkStep st;
-          walk_step(seq, r, H, pt, &st);
-          CHECK(st.n_first >= 1 && st.n_first <= 4 && st.n_rest >= 1 && st.n_rest <= 2, "segment counts %d %d", st.n_first, st.n_rest);
-          for (int c = 0; c < st.n_claim; ++c) {
-            const long long J = seq * H + st.claim_job[c];
+          M.seq = seq; M.r = r;
+          const WalkWin w = walk_window(seq, r, H, pt);
+          CHECK(w.n >= 1 && w.n <= kWalkKH && w.n1 >= 1 && w.n1 <= w.n && w.n_fresh >= 0 && w.n_fresh <= w.n, "window");
+          for (int c = 0; c < w.n_fresh; ++c) {
+            const long long J = seq * H + w.o_lo + w.n - w.n_fresh + c;
             Slot& s = ring[J % kWalkSlots];
             // the issuer blocks until the epilogue has freed the slot: that needs the previous owner to be
             // published by an EARLIER step, otherwise the kernel deadlocks
@@ -77,18 +83,19 @@ int main() {
             s.published = false;
             s.terms.clear();
           }
-          std::set<std::pair<int, int>> covered;
-          apply(st.first, st.n_first, true, seq, r, H, pt, ring, &covered);
-          apply(st.rest, st.n_rest, false, seq, r, H, pt, ring, &covered);
-          CHECK(covered.empty(), "first list covers blocks the rest list does not");
+          int n_first = 0, n_rest = 0;
+          walk_segments(w, true, [&](int slot, int bi, int nb, int fresh) { M.mma(slot, bi, nb, fresh, true); ++n_first; });
+          walk_segments(w, false, [&](int slot, int bi, int nb, int fresh) { M.mma(slot, bi, nb, fresh, false); ++n_rest; });
+          CHECK(M.covered.empty(), "first list covers blocks the rest list does not");
+          CHECK(n_first >= 1 && n_first <= 4 && n_rest >= 1 && n_rest <= 2, "segment counts %d %d", n_first, n_rest);
           // every kernel row that sees input row r inside the image was issued
           for (int kh = 0; kh < kWalkKH; ++kh) {
             const int o = r - kh + pt;
             if (o < 0 || o >= H) continue;
             CHECK(ring[(seq * H + o) % kWalkSlots].terms.count({r, kh}) == 1, "missing product r %d kh %d", r, kh);
           }
-          for (int d = 0; d < st.n_done; ++d) {
-            const int o = st.done_job[d];
+          for (int d = 0; d < w.n_done; ++d) {
+            const int o = w.done_lo + d;
             const long long J = seq * H + o;
             Slot& s = ring[J % kWalkSlots];
             CHECK(s.job == J && !s.published, "publish of a job that is not live");
@@ -103,8 +110,8 @@ int main() {
             s.published = true;
           }
           ++steps;
-          mmas_first += st.n_first;
-          mmas_rest += st.n_rest;
+          mmas_first += n_first;
+          mmas_rest += n_rest;
         }
         CHECK(published_upto == (seq + 1) * H - 1, "tile %lld left unpublished rows", seq);
       }
