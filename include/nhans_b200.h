@@ -139,6 +139,10 @@ int nhans_profile_get_layer(nhans_ctx* ctx, int net, int layer, double* stats);
 const char* nhans_plan_json(nhans_ctx* ctx, int net);
 /* Copy activation buffer `buf` of net (fp16 bits) to the host: n_elems must not exceed its size. */
 int nhans_debug_read_buffer(nhans_ctx* ctx, int net, int buf, uint16_t* out, int64_t n_elems);
+/* Debug: the spectra the fused path keeps in HBM for the batch nhans_run just processed (tests compare them with
+ * the oracle's SN/apply.py:368-375 arrays): which 0 = log-magnitude [frames][201], 1 = unit phasors X / |X|
+ * [frames][201][2] (the fused path stores phasors instead of angles), 2 = denoised log-magnitude [frames][201]. */
+int nhans_debug_read_batch(nhans_ctx* ctx, int which, float* out, int64_t n_floats);
 /* Debug: accumulated wait cycles of one tensor-core layer (needs NHANS_DEBUG_STATS=1 at create time):
  * {MMA waits accumulator free, MMA waits A, MMA waits B, epilogue waits accumulator ready, MMA warp total, ...}. */
 int nhans_debug_layer_stats(nhans_ctx* ctx, int net, int layer, uint64_t* out8);

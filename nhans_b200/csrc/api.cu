@@ -339,6 +339,7 @@ EpiDev make_epi(const NetDev& net, const Epilogue& E, const Grid& out, const flo
     e.res_C = net.plan.bufs[E.res_buf].C;
     e.res_scale = res_scale;
   }
+  if (E.head) e.res_scale = res_scale;      // head: inverse of the per-column weight scale
   e.r1_vec = r1_vec; e.r1_sh = E.r1_sh; e.r1_sw = E.r1_sw; e.raw_oh = E.raw_oh;
   e.raw = raw;
   e.relu = E.relu; e.head = E.head;
@@ -489,8 +490,13 @@ int ensure_silent(nhans_ctx* ctx) {
 }
 
 int check_kernel_flag(nhans_ctx* ctx) {
-  if (ctx->err_flag_host && *ctx->err_flag_host)
-    return fail(ctx, NHANS_ERR_KERNEL, "GEMM pipeline timed out waiting on barrier class " + std::to_string(*ctx->err_flag_host));
+  if (ctx->err_flag_host && *ctx->err_flag_host) {
+    // reported once: the flag is cleared so that a later call (after nhans_load_weights, or on a context whose
+    // launch merely failed) is judged on its own; a trapped kernel leaves the CUDA context unusable anyway
+    const int tag = *ctx->err_flag_host;
+    *ctx->err_flag_host = 0;
+    return fail(ctx, NHANS_ERR_KERNEL, "tensor-core pipeline timed out waiting on barrier class " + std::to_string(tag));
+  }
   return 0;
 }
 
@@ -604,7 +610,13 @@ int nhans_load_weights(nhans_ctx* ctx, const char* const* names, const int64_t* 
   if ((rc = realise_net(ctx, ctx->tower))) return rc;
   // the packed host copies are no longer needed
   for (NetDev* nd : {&ctx->main_net, &ctx->tower})
-    for (auto& L : nd->plan.gemm) std::vector<uint16_t>().swap(L.w);
+    for (auto& L : nd->plan.gemm) {
+      if (L.subnormal_frac > 0.01)
+        fprintf(stderr, "nhans: warning: %.1f %% of the fp16 weights of layer %s are subnormal (reduced precision)\n",
+                100.0 * L.subnormal_frac, L.name.c_str());
+      std::vector<uint16_t>().swap(L.w);
+    }
+  if (ctx->err_flag_host) *ctx->err_flag_host = 0;
   return NHANS_OK;
 }
 
@@ -628,7 +640,7 @@ int nhans_normalise(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int
     oo[u + 1] = oo[u] + n;
   }
   const long long total = ho[U] - ho[0];
-  CK(ctx->tmp[0].ensure(total * 2 + 2));
+  CK(ctx->tmp[0].ensure(total * 2 + 32));
   CK(cudaMemcpyAsync(ctx->tmp[0].p, pcm + ho[0], total * 2, cudaMemcpyHostToDevice, ctx->stream));
   std::vector<long long> rel(U + 1);
   for (int u = 0; u <= U; ++u) rel[u] = ho[u] - ho[0];
@@ -661,7 +673,7 @@ int nhans_stft(nhans_ctx* ctx, const int16_t* pcm, const int64_t* offs, int U, f
   for (int u = 0; u <= U; ++u) frame_offs[u] = fo[u];
   if (!logmag && !phase && !peak) return NHANS_OK;
   const long long total = rel[U];
-  CK(ctx->tmp[0].ensure(total * 2 + 2));
+  CK(ctx->tmp[0].ensure(total * 2 + 32));
   CK(cudaMemcpyAsync(ctx->tmp[0].p, pcm + offs[0], total * 2, cudaMemcpyHostToDevice, ctx->stream));
   int rc;
   if ((rc = to_device_offs(ctx, ctx->tmp[1], rel))) return rc;
@@ -860,12 +872,12 @@ int nhans_upload(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, in
   for (int u = 0; u <= U; ++u) b.ctx_frame_offs[u] = (long long)u * kCtxFrames;
   b.total_frames = b.frame_offs[U];
   b.total_out = b.out_offs[U];
-  CK(b.mix.ensure(b.mix_offs[U] * 2 + 2));
+  CK(b.mix.ensure(b.mix_offs[U] * 2 + 32));
   CK(cudaMemcpyAsync(b.mix.p, mix + mix_offs[0], b.mix_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
-  CK(b.b.ensure(b.b_offs[U] * 2 + 2));
+  CK(b.b.ensure(b.b_offs[U] * 2 + 32));
   CK(cudaMemcpyAsync(b.b.p, ctx_b + b_offs[0], b.b_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
   if (b.has_a) {
-    CK(b.a.ensure(b.a_offs[U] * 2 + 2));
+    CK(b.a.ensure(b.a_offs[U] * 2 + 32));
     CK(cudaMemcpyAsync(b.a.p, ctx_a + a_offs[0], b.a_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = to_device_offs(ctx, b.d_a_offs, b.a_offs))) return rc;
   }
@@ -897,7 +909,7 @@ int nhans_run(nhans_ctx* ctx) {
   CK(b.ctxlm_b.ensure(cbytes));
   CK(b.emb_b.ensure((size_t)U * 512 * 4));
   CK(b.cond.ensure((size_t)U * n_cols * 4));
-  CK(b.out_i16.ensure(b.total_out * 2 + 2));
+  CK(b.out_i16.ensure(b.total_out * 2 + 32));
   CK(b.out_f32.ensure(b.total_out * 4 + 4));
   CK(b.mixproc.ensure(b.total_out * 4 + 4));
   if (!b.has_a && (rc = ensure_silent(ctx))) return rc;
@@ -1100,6 +1112,20 @@ int nhans_debug_read_buffer(nhans_ctx* ctx, int net, int buf, uint16_t* out, int
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, nd.bufs[buf], (size_t)n_elems * 2, cudaMemcpyDeviceToHost));
+  return NHANS_OK;
+}
+
+int nhans_debug_read_batch(nhans_ctx* ctx, int which, float* out, int64_t n_floats) {
+  if (!ctx || !out || which < 0 || which > 2) return NHANS_ERR_ARG;
+  Batch& b = ctx->batch;
+  if (!b.done) return fail(ctx, NHANS_ERR_STATE, "nhans_run has not produced a batch");
+  const long long rows = b.total_frames * kBins;
+  const long long have = which == 1 ? 2 * rows : rows;            // 1: unit phasors (float2 per bin)
+  if (n_floats > have) return fail(ctx, NHANS_ERR_ARG, "the batch holds fewer values than requested");
+  const DBuf& src = which == 0 ? b.logmag : (which == 1 ? b.phase : b.den);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, src.p, (size_t)n_floats * 4, cudaMemcpyDeviceToHost));
   return NHANS_OK;
 }
 

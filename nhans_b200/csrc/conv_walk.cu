@@ -158,30 +158,34 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const uint32_t a_lo = a_base + aslot * (kSlabBytes >> 4);
         const uint64_t da0 = desc_hi | (uint64_t)a_lo;
         const uint64_t db0 = desc_hi | (uint64_t)b_base;
-        // K step 0 (tap 0, k = 0): fresh slots do not accumulate
+        // one elected lane issues the whole step: K step 0 (tap 0, k = 0) apart, because fresh slots must not
+        // accumulate; the other 15 K steps are one MMA over the whole window, two where the slot ring wraps
         if (ptx::elect_one()) {
           walk_segments(w, true, [&](int slot, int bi, int nb, int fresh) {
             ptx::umma_f16(tmem_base + (uint32_t)slot * 64, da0, db0 + (uint64_t)(bi * ((64 * 128) >> 4)),
                           idesc0 | ((uint32_t)(nb * 64 >> 3) << 17), fresh ? 0u : 1u);
           });
+          const uint32_t d_a = tmem_base + (uint32_t)w.slot0 * 64, d_b = tmem_base;
+          const uint32_t i_a = idesc0 | ((uint32_t)(w.n1 * 64 >> 3) << 17), i_b = idesc0 | ((uint32_t)((w.n - w.n1) * 64 >> 3) << 17);
+          const uint64_t db_a = db0 + (uint64_t)(w.bi0 * ((64 * 128) >> 4)), db_b = db_a + (uint64_t)(w.n1 * ((64 * 128) >> 4));
+          if (w.n == w.n1) {
+#pragma unroll
+            for (int kk = 1; kk < kWalkKW * 4; ++kk) {
+              const int kw = kk >> 2, k = kk & 3;                                  // tap kw = slab rows shifted by kw
+              ptx::umma_f16(d_a, da0 + (uint64_t)(kw * 8 + 2 * k), db_a + (uint64_t)(kw * (kBTile >> 4) + 2 * k), i_a, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 1; kk < kWalkKW * 4; ++kk) {
+              const int kw = kk >> 2, k = kk & 3;
+              const uint64_t da = da0 + (uint64_t)(kw * 8 + 2 * k);
+              const uint64_t bo = (uint64_t)(kw * (kBTile >> 4) + 2 * k);
+              ptx::umma_f16(d_a, da, db_a + bo, i_a, 1u);
+              ptx::umma_f16(d_b, da, db_b + bo, i_b, 1u);
+            }
+          }
         }
         __syncwarp();
-        // the other 15 K steps: one MMA over the whole window, two where the slot ring wraps
-        const uint32_t d_a = tmem_base + (uint32_t)w.slot0 * 64, d_b = tmem_base;
-        const uint32_t i_a = idesc0 | ((uint32_t)(w.n1 * 64 >> 3) << 17), i_b = idesc0 | ((uint32_t)((w.n - w.n1) * 64 >> 3) << 17);
-        const uint64_t db_a = db0 + (uint64_t)(w.bi0 * ((64 * 128) >> 4)), db_b = db_a + (uint64_t)(w.n1 * ((64 * 128) >> 4));
-        const bool two = w.n > w.n1;
-#pragma unroll
-        for (int kk = 1; kk < kWalkKW * 4; ++kk) {
-          const int kw = kk >> 2, k = kk & 3;
-          if (ptx::elect_one()) {
-            const uint64_t da = da0 + (uint64_t)(kw * 8 + 2 * k);                 // tap kw = slab rows shifted by kw
-            const uint64_t bo = (uint64_t)(kw * (kBTile >> 4) + 2 * k);
-            ptx::umma_f16(d_a, da, db_a + bo, i_a, 1u);
-            if (two) ptx::umma_f16(d_b, da, db_b + bo, i_b, 1u);
-          }
-          __syncwarp();
-        }
         if (ptx::elect_one()) {
           ptx::umma_commit(&ctrl->a_empty[aslot]);
           for (int d = 0; d < w.n_done; ++d) ptx::umma_commit(&ctrl->tmem_full[(j0 + w.done_lo + d) & (kWalkSlots - 1)]);

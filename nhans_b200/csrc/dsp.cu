@@ -18,7 +18,7 @@
 //            lanes walk consecutive bins so that the global stores are coalesced
 // One 1.6 KB buffer per frame is the whole working set (pass A and B run in place).  The forward kernel stages the
 // int16 span of its 16 frames with one 1-D bulk TMA copy (cp.async.bulk, mbarrier completion) and converts each
-// sample once; the inverse kernel gathers 30 output hops from 32 frames and writes 128-bit / 64-bit vectors.
+// sample once; the inverse kernel gathers 26 output hops from 28 frames and writes 128-bit / 64-bit vectors.
 #include "kernels.h"
 #include "fft400.cuh"
 #include "ptx.cuh"
@@ -37,10 +37,10 @@ constexpr int kFW = 4;                  // frames per warp
 constexpr int kSW = 4;                  // warps per CTA (forward)
 constexpr int kFB = kFW * kSW;          // frames per CTA (forward)
 constexpr int kSpanF = (kFB - 1) * kHop + kWin;
-constexpr int kIW = 8;                  // warps per CTA (inverse)
+constexpr int kIW = 7;                  // warps per CTA (inverse): 28 frames x 1.6 KB stay under the 48 KB static limit
 constexpr int kNFI = kFW * kIW;         // frames per CTA (inverse)
-constexpr int kOH = kNFI - 2;           // output hops per CTA (2 of 32 frames are recomputed by the neighbour)
-constexpr int kThreads = 256;           // inverse kernels
+constexpr int kOH = kNFI - 2;           // output hops per CTA (2 of 28 frames are recomputed by the neighbour)
+constexpr int kThreads = kIW * 32;      // inverse kernels
 
 __device__ float2 g_tw200[200];         // e^{-2 pi i t / 200}
 __device__ float2 g_tw400[201];         // e^{-2 pi i k / 400}
@@ -139,7 +139,7 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
       ptx::mbar_expect_tx(&s_bar, bytes);
       ptx::bulk_load_1d(s_raw, pcm + abase, bytes, &s_bar);
     }
-    while (!ptx::mbar_try_wait(&s_bar, 0)) {}
+    ptx::mbar_wait(&s_bar, 0, nullptr, 7);          // bounded: traps instead of hanging if the copy never lands
     // x / (peak + 1e-6) in float64 like the reference, as a multiplication by the float64 reciprocal (differs from
     // the true quotient by < 1 float64 ulp before the rounding to float32; nhans_normalise keeps the exact division)
     const double inv = 1.0 / ((double)peak[u] + 0.000001);
@@ -462,8 +462,8 @@ cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase
   (void)total_blocks_hint;
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + 2 + kOH - 1) / kOH, U);
-  if (phasor) istft_kernel<true><<<grid, kSW * 32, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
-  else istft_kernel<false><<<grid, kSW * 32, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  if (phasor) istft_kernel<true><<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
+  else istft_kernel<false><<<grid, kThreads, 0, s>>>(logmag, phase, frame_offs, out_offs, peak, out_f32, out_i16);
   return cudaGetLastError();
 }
 

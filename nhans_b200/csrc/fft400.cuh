@@ -111,6 +111,32 @@ NHANS_HD void fft200_step_b2(const float2* g, float2* out, int f, int k1, int c)
   o[8 * c] = z0; o[8 * (c + 5)] = z1; o[8 * (c + 10)] = z2; o[8 * (c + 15)] = z3; o[8 * (c + 20)] = z4;
 }
 
+// DFT-25 of 25 values held in registers, in place (two radix-5 stages, compile-time twiddles): y[5 a + b] in, the
+// output for k2 = c + 5 d is left at y[5 c + d].
+template <bool INV>
+NHANS_HD void dft25(float2 (&y)[25]) {
+  const float2 W[17] = {  // e^{-2 pi i j / 25}, j = 0 .. 16
+      {1.000000000e+00f, -0.000000000e+00f}, {9.685831611e-01f, -2.486898872e-01f}, {8.763066800e-01f, -4.817536741e-01f},
+      {7.289686274e-01f, -6.845471059e-01f}, {5.358267950e-01f, -8.443279255e-01f}, {3.090169944e-01f, -9.510565163e-01f},
+      {6.279051953e-02f, -9.980267284e-01f}, {-1.873813146e-01f, -9.822872507e-01f}, {-4.257792916e-01f, -9.048270525e-01f},
+      {-6.374239897e-01f, -7.705132428e-01f}, {-8.090169944e-01f, -5.877852523e-01f}, {-9.297764859e-01f, -3.681245527e-01f},
+      {-9.921147013e-01f, -1.253332336e-01f}, {-9.921147013e-01f, 1.253332336e-01f}, {-9.297764859e-01f, 3.681245527e-01f},
+      {-8.090169944e-01f, 5.877852523e-01f}, {-6.374239897e-01f, 7.705132428e-01f}};
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {       // g[b][c] = W25^{bc} sum_a y[5a + b] W5^{ac}, stored at y[5 c + b]
+    float2 o0, o1, o2, o3, o4;
+    dft5<INV>(y[b], y[5 + b], y[10 + b], y[15 + b], y[20 + b], o0, o1, o2, o3, o4);
+    y[b] = o0;
+    y[5 + b] = b ? cmul(o1, tw<INV>(W[b])) : o1;
+    y[10 + b] = b ? cmul(o2, tw<INV>(W[2 * b])) : o2;
+    y[15 + b] = b ? cmul(o3, tw<INV>(W[3 * b])) : o3;
+    y[20 + b] = b ? cmul(o4, tw<INV>(W[4 * b])) : o4;
+  }
+#pragma unroll
+  for (int c = 0; c < 5; ++c)         // Z[c + 5 d] = sum_b g[b][c] W5^{bd}, stored at y[5 c + d]
+    dft5<INV>(y[5 * c], y[5 * c + 1], y[5 * c + 2], y[5 * c + 3], y[5 * c + 4], y[5 * c], y[5 * c + 1], y[5 * c + 2], y[5 * c + 3], y[5 * c + 4]);
+}
+
 // rfft-400 bin k (0..200) from the DFT-200 Z of the packed sequence z[m] = x[2m] + i x[2m+1]:
 // X[k] = (Z[k] + conj Z[200-k]) / 2 - (i/2) e^{-2 pi i k / 400} (Z[k] - conj Z[200-k])
 NHANS_HD float2 rfft_post(const float2* Z, int k, const float2* tw400) {

@@ -307,12 +307,13 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
           if (kHead) {
             const int col = col0 + c0;
             const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(e.res_scale + col));   // inverse weight scale of the column
             const float* raw_row = e.raw + o_bias[g] - col0;
             float* o = e.out_f32 + o_out[g] - col0;
-            if (col < 201) o[col] = f.x + b.x + raw_row[col];
-            if (col + 1 < 201) o[col + 1] = f.y + b.y + raw_row[col + 1];
-            if (col + 2 < 201) o[col + 2] = f.z + b.z + raw_row[col + 2];
-            if (col + 3 < 201) o[col + 3] = f.w + b.w + raw_row[col + 3];
+            if (col < 201) o[col] = f.x * sc.x + b.x + raw_row[col];
+            if (col + 1 < 201) o[col + 1] = f.y * sc.y + b.y + raw_row[col + 1];
+            if (col + 2 < 201) o[col + 2] = f.z * sc.z + b.z + raw_row[col + 2];
+            if (col + 3 < 201) o[col + 3] = f.w * sc.w + b.w + raw_row[col + 3];
             continue;
           }
           if (p.debug_skip_epilogue != 2) { f.x += L.b[g].x; f.y += L.b[g].y; f.z += L.b[g].z; f.w += L.b[g].w; }

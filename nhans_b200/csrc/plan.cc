@@ -477,6 +477,14 @@ void build_blocks(Builder* B, const std::vector<BlockSpec>& blocks, int H, int W
 }  // namespace
 
 void build_groups(GemmLayer* L) {
+  // fraction of the non-zero packed weights that fell into the fp16 subnormal range (reported at load time)
+  size_t nz = 0, sub = 0;
+  for (uint16_t h : L->w) {
+    if ((h & 0x7fffu) == 0) continue;
+    ++nz;
+    if ((h & 0x7c00u) == 0) ++sub;
+  }
+  L->subnormal_frac = nz ? (double)sub / (double)nz : 0.0;
   L->groups.clear();
   const int n = (int)L->kb.size();
   std::vector<char> used(n, 0);
@@ -587,8 +595,23 @@ NetPlan build_main_plan(const WeightMap& w, int variant, int capacity) {
     L.N = 208; L.BN = 208; L.K = 13312;
     for (int k = 0; k < 13312; k += kTileK) L.kb.push_back({0, 0, (int16_t)k});
     L.w.assign((size_t)208 * 13312, 0);
-    for (int n = 0; n < kBins; ++n)
-      for (int k = 0; k < 13312; ++k) L.w[(size_t)n * 13312 + k] = f32_to_f16_bits(wd[(size_t)k * kBins + n]);
+    // last_dense is zero-initialised and trained with a small learning rate (main.py:238): real checkpoints may
+    // hold values below the fp16 normal range (6.1e-5).  Every output column is therefore scaled by a power of
+    // two that brings its largest weight into [0.5, 1) before the cast (exact in fp32), and the head epilogue
+    // multiplies the accumulator by the inverse (epi.res_scale doubles as that per-column factor for the head).
+    L.epi.res_scale.assign(208, 1.f);
+    for (int n = 0; n < kBins; ++n) {
+      float mx = 0.f;
+      for (int k = 0; k < 13312; ++k) mx = std::max(mx, std::fabs(wd[(size_t)k * kBins + n]));
+      int e = 0;
+      if (mx > 0.f && std::isfinite(mx)) {
+        std::frexp(mx, &e);                              // mx = m * 2^e, m in [0.5, 1)
+        e = std::min(std::max(-e, -24), 40);             // scale 2^-e, bounded
+      }
+      const float sc = std::ldexp(1.f, e);
+      L.epi.res_scale[n] = std::ldexp(1.f, -e);
+      for (int k = 0; k < 13312; ++k) L.w[(size_t)n * 13312 + k] = f32_to_f16_bits(wd[(size_t)k * kBins + n] * sc);
+    }
     L.epi.bias.assign(208, 0.f);
     for (int n = 0; n < kBins; ++n) L.epi.bias[n] = bd[n];
     L.epi.relu = 0;

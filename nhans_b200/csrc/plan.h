@@ -103,7 +103,8 @@ struct Epilogue {
   int pair_W = 0;                 // logical width: pixel j of a pair is valid when 2 w' + j < pair_W
   int64_t res_off[2] = {0, 0};    // residual row of pixel j relative to the GEMM row
   int relu = 1;
-  int head = 0;                   // 1: fp32 output [n][201] = acc + bias + raw[center frame] (main.py:238-242)
+  int head = 0;                   // 1: fp32 output [n][201] = acc * res_scale + bias + raw[center frame] (main.py:238-242;
+                                  //    res_scale = inverse of the per-column power-of-two weight scale)
 };
 
 struct GemmLayer {
@@ -124,6 +125,7 @@ struct GemmLayer {
   // engine repacks the weights as [kernel row block][cout] x [kw][cin] and walks the image rows instead.
   int walk = 0;
   int c_kh = 0, c_kw = 0, c_pt = 0, c_pl = 0;
+  double subnormal_frac = 0;              // share of the non-zero fp16 weights that are subnormal (precision warning)
 };
 
 struct DirectLayer {

@@ -97,8 +97,8 @@ class Engine:
         self._ck(self.lib.nhans_load_weights(self.h, c_names, c_sizes, c_data, len(names)))
         self.weight_source = source
 
-    def load_default_weights(self, model_dir=None, seed=0):
-        w, src = W.load_or_init(self.variant, model_dir, seed)
+    def load_default_weights(self, model_dir=None, seed=0, allow_random=None):
+        w, src = W.load_or_init(self.variant, model_dir, seed, allow_random)
         self.load_weights(w, src)
         return src
 
@@ -158,6 +158,36 @@ class Engine:
         y, _ = self.istft(den, sp, f1)
         ymix, _ = self.istft(sl, sp, f1)
         return y, ymix
+
+    def enhance_float(self, mix, ctx_a, ctx_b):
+        """apply_snc / apply_separator for clips that are not int16 PCM (stereo files averaged in float64,
+        SN/apply.py:46-53): host normalisation exactly like handle_signals (SN/apply.py:142-163), then the stage entry
+        points - float STFT, towers on the first 200 context frames, mask network over every frame, inverse STFT.
+        ctx_a may be None (Silent.wav).  -> dict(f32=denoised samples, mixed_processed=..., peak=max|mix|)."""
+        from .wavio import normalise_host
+        m = normalise_host(mix)
+        if len(m) >= 400:
+            m = m[:len(m) - (len(m) - 400) % 160]
+        sigs = [m, normalise_host(ctx_b)] + ([normalise_host(ctx_a)] if ctx_a is not None else [])
+        lm, ph, fo = self.stft_f32(sigs)
+        T = int(fo[1])
+        if T <= 0:
+            z = np.zeros(0, np.float32)
+            return dict(f32=z, mixed_processed=z, peak=0.0)
+        for u in range(1, len(sigs)):
+            if fo[u + 1] - fo[u] < CTX_FRAMES:
+                raise NhansError(-4, "context clip yields %d < 200 STFT frames (needs >= 32240 samples)" % (fo[u + 1] - fo[u]))
+        ctx_b_lm = lm[fo[1]:fo[1] + CTX_FRAMES]
+        ctx_a_lm = (lm[fo[2]:fo[2] + CTX_FRAMES] if ctx_a is not None
+                    else np.full((CTX_FRAMES, N_BINS), np.log(np.float32(1e-5)), np.float32))     # all-zero Silent.wav
+        emb = self.embed(np.stack([ctx_a_lm, ctx_b_lm]))
+        sl, sp = np.ascontiguousarray(lm[:T]), np.ascontiguousarray(ph[:T])
+        f1 = np.array([0, T], np.int64)
+        den = self.masknet(sl, f1, emb[0:1], emb[1:2])
+        y, _ = self.istft(den, sp, f1)
+        ymix, _ = self.istft(sl, sp, f1)
+        x = np.asarray(mix)
+        return dict(f32=y, mixed_processed=ymix, peak=float(max(abs(x))) if len(x) else 0.0)
 
     def eval_loss(self, denoised, target):
         """example_loss of the model graph (SN/main.py:243-246): [n,201] x [n,201] -> [n]."""
@@ -318,6 +348,17 @@ class Engine:
         out = np.zeros(n, np.uint16)
         self._ck(self.lib.nhans_debug_read_buffer(self.h, net, buf, _ptr(out), n))
         return out.view(np.float16).reshape(g["pixels"], g["C"])
+
+    def read_batch_spectra(self, n_frames):
+        """Fused path introspection: (logmag [F,201], unit phasors [F,201,2], denoised logmag [F,201]) of the batch
+        just processed, as kept in HBM between the kernels."""
+        lm = np.zeros((n_frames, N_BINS), np.float32)
+        ph = np.zeros((n_frames, N_BINS, 2), np.float32)
+        den = np.zeros((n_frames, N_BINS), np.float32)
+        self._ck(self.lib.nhans_debug_read_batch(self.h, 0, _ptr(lm), lm.size))
+        self._ck(self.lib.nhans_debug_read_batch(self.h, 1, _ptr(ph), ph.size))
+        self._ck(self.lib.nhans_debug_read_batch(self.h, 2, _ptr(den), den.size))
+        return lm, ph, den
 
     def device_info(self):
         sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()

@@ -21,7 +21,7 @@ import numpy as np
 
 from .. import weights as W
 from ..session import get_engine
-from ..wavio import FS, read_wav, write_wav
+from ..wavio import FS, is_pcm16, normalise_host, read_wav, write_wav
 
 Noise_Win = 200      # SN/apply.py:37
 Mix_Win = 35         # SN/apply.py:38
@@ -46,10 +46,16 @@ FLAGS = _Flags()
 def handle_signals(mixedpath, noisepospath, noisenegpath):
     """SN/apply.py:142-163: (pos, neg, mixed) peak-normalised float32, the mixture trimmed to whole frames."""
     eng = get_engine(VARIANT)
-    mixed = eng.normalise([read_wav(mixedpath)], trim=True)[0]
-    pos = eng.normalise([read_wav(noisepospath)], trim=False)[0]
-    neg = eng.normalise([read_wav(noisenegpath)], trim=False)[0]
-    return pos, neg, mixed
+
+    def norm(path, trim):
+        x = read_wav(path)
+        if is_pcm16(x):
+            return eng.normalise([x], trim=trim)[0]
+        y = normalise_host(x)                                      # stereo file: float64 mean, normalised on the host
+        if trim and len(y) >= 400:
+            y = y[:len(y) - (len(y) - 400) % 160]
+        return y
+    return norm(noisepospath, False), norm(noisenegpath, False), norm(mixedpath, True)
 
 
 def _seq_sum(x):
@@ -85,9 +91,7 @@ def domixing(cleansamples, noisepossamples, noisenegsamples, snr_pos, snr_neg):
     return mixed, target, K_pos, K_neg, noise_pos_scaled / d, noise_neg_scaled / d
 
 
-def _norm64(pcm):
-    x = np.asarray(pcm)
-    return (x / (float(max(abs(x))) + 0.000001)).astype(np.float32)
+_norm64 = normalise_host
 
 
 def combine_signals(cleanpath, noisepospath, noisenegpath):
@@ -146,29 +150,59 @@ def _emit(save_to, f32, peak, as_float32):
         write_wav(save_to, np.clip(v, -32768, 32767).astype(np.int16))
 
 
+def _post_mix_host(den, mixed, compensate, ac):
+    # SN/apply.py:459-470 for the (rare) clips that take the float path
+    removed = mixed - den
+    with np.errstate(divide="ignore", invalid="ignore"):
+        snr_est = float(np.mean(den.astype(np.float64) ** 2) / np.mean(removed.astype(np.float64) ** 2)) if len(den) else float("inf")
+    factor = snr_est / 20.0 if ac else compensate
+    if not np.isfinite(factor):
+        factor = 0.0
+    return removed, snr_est, (den + removed * np.float32(factor)).astype(np.float32)
+
+
 def apply_snc_batch(mixedpaths, pospaths, negpaths, save_tos, compensate=None, ac=None, out_format=None):
-    """apply_snc for many files in one GPU batch (folder mode).  pospaths entries may be None / Silent.wav."""
+    """apply_snc for many files in one GPU batch (folder mode).  pospaths entries may be None / Silent.wav: those
+    utterances are conditioned on the all-zero Silent context (SN/apply.py:478-481), whatever the others use."""
     compensate = FLAGS.compensate if compensate is None else compensate
     ac = FLAGS.ac if ac is None else ac
     as_f32 = (FLAGS.float32 if out_format is None else out_format == "float32")
     eng = get_engine(VARIANT)
     mixes = [read_wav(p) for p in mixedpaths]
     negs = [read_wav(p) for p in negpaths]
-    all_silent = all(_is_silent(p) for p in pospaths)
-    poss = None if all_silent else [read_wav(p) for p in pospaths]
-    res = eng.enhance(mixes, poss, negs, want_f32=True, want_i16=False)
-    # removed / snr_est / compensated (SN/apply.py:459-470) come from one fused GPU pass over the batch
-    post = eng.postmix(res["out_offs"], compensate=compensate, ac=ac)
+    silent = [_is_silent(p) for p in pospaths]
+    poss = [None if sil else read_wav(p) for p, sil in zip(pospaths, silent)]
+    U = len(mixes)
+    # int16 PCM clips go through the fused batch entry point; a clip set with a stereo file (float64 mean) takes the
+    # float entry points one utterance at a time
+    pcm = [u for u in range(U) if is_pcm16(mixes[u]) and is_pcm16(negs[u]) and (poss[u] is None or is_pcm16(poss[u]))]
+    out = [None] * U
+    if pcm:
+        if all(silent[u] for u in pcm):
+            pos_clips = None                                       # the engine's cached Silent.wav embedding
+        else:
+            zero = np.zeros(3 * FS, np.int16)                      # Silent.wav stand-in: >= 32240 samples of digital silence
+            pos_clips = [zero if poss[u] is None else poss[u] for u in pcm]
+        res = eng.enhance([mixes[u] for u in pcm], pos_clips, [negs[u] for u in pcm], want_f32=True, want_i16=False)
+        # removed / snr_est / compensated (SN/apply.py:459-470) come from one fused GPU pass over the batch
+        post = eng.postmix(res["out_offs"], compensate=compensate, ac=ac)
+        for j, u in enumerate(pcm):
+            out[u] = (res["f32"][j], post["mixed_processed"][j], post["removed"][j], float(post["snr_est"][j]), post["compensated"][j],
+                      float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0)
+    for u in range(U):
+        if out[u] is None:
+            r = eng.enhance_float(mixes[u], poss[u], negs[u])
+            removed, snr_est, comp = _post_mix_host(r["f32"], r["mixed_processed"], compensate, ac)
+            out[u] = (r["f32"], r["mixed_processed"], removed, snr_est, comp, r["peak"])
     snrs = []
     for u, save_to in enumerate(save_tos):
-        peak = float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0
-        _emit(save_to, res["f32"][u], peak, as_f32)
-        _emit(_sibling(save_to, "mixed_processed.wav"), post["mixed_processed"][u], peak, as_f32)
-        _emit(_sibling(save_to, "removed.wav"), post["removed"][u], peak, as_f32)
-        snr_est = float(post["snr_est"][u])
+        den, mixed, removed, snr_est, comp, peak = out[u]
+        _emit(save_to, den, peak, as_f32)
+        _emit(_sibling(save_to, "mixed_processed.wav"), mixed, peak, as_f32)
+        _emit(_sibling(save_to, "removed.wav"), removed, peak, as_f32)
         print(snr_est)
         print("---------------------------")
-        _emit(_sibling(save_to, "compensated.wav"), post["compensated"][u], peak, as_f32)
+        _emit(_sibling(save_to, "compensated.wav"), comp, peak, as_f32)
         snrs.append(snr_est)
     return snrs
 

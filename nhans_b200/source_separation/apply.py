@@ -15,7 +15,7 @@ import numpy as np
 
 from .. import weights as W
 from ..session import get_engine
-from ..wavio import FS, read_wav, write_wav
+from ..wavio import FS, is_pcm16, read_wav, write_wav
 from ..selective_noise.apply import _emit, _fit_noise, _norm64, _seq_sum, _sibling
 
 Noise_Win = 200
@@ -96,11 +96,22 @@ def apply_separator_batch(mixedpaths, cleanpaths, noisepaths, save_tos, out_form
     mixes = [read_wav(p) for p in mixedpaths]
     cleans = [read_wav(p) for p in cleanpaths]
     noises = [read_wav(p) for p in noisepaths]
-    res = eng.enhance(mixes, noises, cleans, want_f32=True, want_i16=False, want_mixproc=True)   # ctx_a = --neg, ctx_b = --pos
+    U = len(mixes)
+    pcm = [u for u in range(U) if is_pcm16(mixes[u]) and is_pcm16(cleans[u]) and is_pcm16(noises[u])]
+    out = [None] * U
+    if pcm:
+        res = eng.enhance([mixes[u] for u in pcm], [noises[u] for u in pcm], [cleans[u] for u in pcm],
+                          want_f32=True, want_i16=False, want_mixproc=True)                       # ctx_a = --neg, ctx_b = --pos
+        for j, u in enumerate(pcm):
+            out[u] = (res["f32"][j], res["mixed_processed"][j], float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0)
+    for u in range(U):
+        if out[u] is None:                                         # a stereo file in the set: float entry points
+            r = eng.enhance_float(mixes[u], noises[u], cleans[u])
+            out[u] = (r["f32"], r["mixed_processed"], r["peak"])
     for u, save_to in enumerate(save_tos):
-        peak = float(max(abs(mixes[u]))) if len(mixes[u]) else 0.0
-        _emit(save_to, res["f32"][u], peak, as_f32)
-        _emit(_sibling(save_to, "mixed_processed.wav"), res["mixed_processed"][u], peak, as_f32)
+        den, mixed, peak = out[u]
+        _emit(save_to, den, peak, as_f32)
+        _emit(_sibling(save_to, "mixed_processed.wav"), mixed, peak, as_f32)
 
 
 def apply_separator(mixedpath, cleanpath, noisepath, save_to):

@@ -249,16 +249,33 @@ def read_bundle_index(index_path):
     return entries
 
 
+class CheckpointMissing(FileNotFoundError):
+    """No usable trained checkpoint (directory absent, no .index, or the data shard is a git-LFS pointer)."""
+
+
+def _is_lfs_pointer(path):
+    try:
+        if os.path.getsize(path) > 1024:
+            return False
+        with open(path, "rb") as f:
+            return f.read(64).startswith(b"version https://git-lfs")
+    except OSError:
+        return False
+
+
 def load_bundle(prefix):
     """Load every float32 tensor of a TF checkpoint ``prefix`` (no TensorFlow needed).
 
-    Raises FileNotFoundError when the data shard is missing or is a git-LFS pointer (the state of
-    the reference mount)."""
+    Raises CheckpointMissing when the data shard is absent or a git-LFS pointer (the state of the reference
+    mount) and ValueError when it exists but is shorter than the index says (a truncated
+    download must not be mistaken for 'no checkpoint')."""
     entries = read_bundle_index(prefix + ".index")
     data_path = prefix + ".data-00000-of-00001"
     need = max(e["offset"] + e["size"] for e in entries.values())
-    if not os.path.exists(data_path) or os.path.getsize(data_path) < need:
-        raise FileNotFoundError("%s is absent or a git-LFS pointer (need %d bytes)" % (data_path, need))
+    if not os.path.exists(data_path) or _is_lfs_pointer(data_path):
+        raise CheckpointMissing("%s is absent or a git-LFS pointer (need %d bytes)" % (data_path, need))
+    if os.path.getsize(data_path) < need:
+        raise ValueError("%s is truncated: %d bytes, the index needs %d" % (data_path, os.path.getsize(data_path), need))
     out = {}
     with open(data_path, "rb") as f:
         for name, e in entries.items():
@@ -281,11 +298,24 @@ def find_checkpoint(model_dir):
     return None
 
 
-def load_or_init(variant=SELECTIVE_NOISE, model_dir=None, seed=0):
-    """Weights from the trained checkpoint when present, else the seeded random init.
+def random_init_allowed():
+    return os.environ.get("NHANS_ALLOW_RANDOM_INIT", "0") not in ("", "0")
+
+
+def load_or_init(variant=SELECTIVE_NOISE, model_dir=None, seed=0, allow_random=None):
+    """Weights from the trained checkpoint under ``model_dir``.
+
+    The reference hard-fails when the checkpoint cannot be restored (SN/apply.py:428-432), and so does this:
+    without a usable checkpoint CheckpointMissing is raised - unless seeded random-init weights of the identical
+    architecture are explicitly allowed (``allow_random=True`` or NHANS_ALLOW_RANDOM_INIT=1; what the tests and
+    the benchmark use, because the mounted checkpoints are git-LFS pointers).  A truncated data shard or a
+    checkpoint with missing variables is always an error.
 
     Returns (weights, source) with source in {'checkpoint', 'random-init'}."""
+    if allow_random is None:
+        allow_random = random_init_allowed()
     prefix = find_checkpoint(model_dir) if model_dir else None
+    why = "no checkpoint (*.index) under %r" % (model_dir,)
     if prefix:
         try:
             w = load_bundle(prefix)
@@ -294,6 +324,9 @@ def load_or_init(variant=SELECTIVE_NOISE, model_dir=None, seed=0):
             if missing:
                 raise KeyError("checkpoint lacks %d variables, e.g. %s" % (len(missing), missing[0]))
             return {n: w[n] for n in want}, "checkpoint"
-        except FileNotFoundError:
-            pass
+        except CheckpointMissing as ex:
+            why = str(ex)
+    if not allow_random:
+        raise CheckpointMissing(why + "; set NHANS_ALLOW_RANDOM_INIT=1 to run with seeded random-init weights of the "
+                                "identical architecture instead")
     return seeded_init(variant, seed), "random-init"

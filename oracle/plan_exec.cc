@@ -69,6 +69,7 @@ void epilogue(const EpiCtx& c, const Epilogue& E, const Grid& out, int N, int Wo
   for (int n = 0; n < N; ++n) {
     float v = acc[n] + bias[n];
     if (!E.tftab.empty()) v += E.tftab[((size_t)ho * Wo + wo) * N + n];
+    if (E.head) v = acc[n] * E.res_scale[n] + bias[n];      // inverse of the per-column weight scale (plan.cc last_dense)
     if (E.res_buf >= 0) v = fmaf(E.res_scale[n], bufs[E.res_buf][(size_t)res_row * c.net->plan.bufs[E.res_buf].C + n], v);
     if (!E.r1_vec.empty()) v = fmaf(E.r1_vec[n], rawv, v);
     if (E.relu) v = v > 0.f ? v : 0.f;

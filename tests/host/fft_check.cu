@@ -34,6 +34,24 @@ int main() {
     if (d > 1e-4) return 2;
     c = c2;
   }
+  {  // the in-register DFT-25 of the warp-per-frame kernels (dft25, output for k2 = c + 5 d left at y[5 c + d])
+    double d = 0;
+    for (int inv = 0; inv < 2; ++inv)
+      for (int f = 0; f < NF; ++f)
+        for (int k1 = 0; k1 < 8; ++k1) {
+          float2 y[25], ref[200] = {};
+          for (int i = 0; i < 25; ++i) y[i] = b[f * 200 + k1 * 25 + i];
+          if (inv) { dft25<true>(y); fft200_step_b<true>(b.data() + f * 200, ref, 0, k1, t25.data()); }
+          else { dft25<false>(y); fft200_step_b<false>(b.data() + f * 200, ref, 0, k1, t25.data()); }
+          for (int c5 = 0; c5 < 5; ++c5)
+            for (int d5 = 0; d5 < 5; ++d5) {
+              const float2 want = ref[k1 + 8 * (c5 + 5 * d5)];
+              d = fmax(d, fmax(fabs(y[5 * c5 + d5].x - want.x), fabs(y[5 * c5 + d5].y - want.y)));
+            }
+        }
+    printf("in-register dft25 max diff %.3e\n", d);
+    if (d > 1e-4) return 3;
+  }
   double max_err = 0, max_mag = 0;
   std::vector<float2> S(NF * 201);
   for (int f = 0; f < NF; ++f)

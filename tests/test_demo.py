@@ -123,6 +123,7 @@ def test_apply_demo_files(tmp_path, monkeypatch):
     monkeypatch.setenv("NHANS_WIN_CAPACITY", "128")
     monkeypatch.setenv("NHANS_ROW_CAPACITY", "2")
     monkeypatch.setenv("NHANS_MODEL_DIR", str(tmp_path / "no_model"))
+    monkeypatch.setenv("NHANS_ALLOW_RANDOM_INIT", "1")            # no checkpoint on the test box: seeded random init
     session.close_all()
     for n, x in (("s", synth.mixture(2.6, 5)), ("p", synth.noise_clip(5, "pos")), ("n", synth.noise_clip(5, "neg")),
                  ("short", synth.mixture(1.5, 6))):

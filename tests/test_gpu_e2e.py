@@ -112,6 +112,7 @@ def test_cli_file_surface(tmp_path, monkeypatch):
     monkeypatch.setenv("NHANS_WIN_CAPACITY", "128")
     monkeypatch.setenv("NHANS_ROW_CAPACITY", "2")
     monkeypatch.setenv("NHANS_MODEL_DIR", str(tmp_path / "no_model"))
+    monkeypatch.setenv("NHANS_ALLOW_RANDOM_INIT", "1")            # no checkpoint on the test box: seeded random init
     session.close_all()
     d = tmp_path
     write_wav(str(d / "mixed.wav"), synth.mixture(0.5, 0))

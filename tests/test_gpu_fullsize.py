@@ -43,7 +43,7 @@ def test_cfg2_denoise_256x4s(big_sn, engine_sn, oracle_sn):
         else:
             first[i] = u
     assert len(first) == 16
-    for i in (0, 9):
+    for i in (0, 5, 9, 14):                            # four distinct utterances against the oracle
         ref = O.apply_arrays(oracle_sn, base_m[i], synth.silence(), base_n[i])
         assert _snr(ref, res["f32"][first[i]]) >= 40.0
     # the same utterance through 256-window passes (single-CTA head, other tile walk)
@@ -85,10 +85,11 @@ def test_cfg4_separator_10s(weights_ss, oracle_ss):
     eng.close()
 
 
-def test_cfg5_shard_512x10s(big_sn):
+def test_cfg5_shard_512x10s(big_sn, oracle_sn):
     """configs[4]: the utterance-sharded sweep gives each of 8 GPUs 1024 x 10 s clips; half such a shard (512 x 10 s,
     0.5 M windows, 250 passes) goes through one nhans_enhance_batch call here.  Copies must come back bit-identical
-    wherever they sit, outputs have the trimmed length, and a clip processed alone gives the same samples."""
+    wherever they sit, outputs have the trimmed length, a clip processed alone gives the same samples, and one 10 s
+    utterance of the batch is compared with the oracle (998 windows)."""
     base_m = [synth.mixture(10.0, 60 + u) for u in range(4)]
     base_n = [synth.noise_clip(60 + u) for u in range(4)]
     order = [(3 * u + 1) % 4 for u in range(512)]
@@ -100,6 +101,10 @@ def test_cfg5_shard_512x10s(big_sn):
             assert np.array_equal(res["i16"][u], res["i16"][first[i]])
         else:
             first[i] = u
-    solo = big_sn.enhance([base_m[2]], None, [base_n[2]], want_f32=False)
+    solo = big_sn.enhance([base_m[2]], None, [base_n[2]], want_f32=True)
     assert np.array_equal(solo["i16"][0], res["i16"][first[2]])
+    ref = O.apply_arrays(oracle_sn, base_m[2], synth.silence(), base_n[2], return_all=True)
+    assert _snr(ref["samples"], solo["f32"][0]) >= 40.0
+    i16 = O.to_int16(ref["samples"], ref["peak"]).astype(np.int32)
+    assert np.abs(res["i16"][first[2]].astype(np.int32) - i16).max() <= max(2, int(3e-3 * np.abs(i16).max()))
     assert np.abs(res["i16"][first[2]].astype(np.int32)).max() > 1000      # not silence

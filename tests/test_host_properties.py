@@ -81,7 +81,7 @@ def test_wav_io_mono_stereo(tmp_path):
     write_wav(p2, stereo)
     got = read_wav(p2)                                                # SN/apply.py:50-51: mean over channels
     want = stereo.astype(np.float64).mean(axis=1)
-    assert got.dtype == np.int16 and np.abs(got - want).max() <= 0.5
+    assert got.dtype == np.float64 and np.array_equal(got, want)      # exact: never rounded back to int16
     silent = np.zeros((1000, 2), np.int16)                            # Silent.wav is stereo zeros
     p3 = str(tmp_path / "z.wav")
     write_wav(p3, silent)

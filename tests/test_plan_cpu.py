@@ -78,3 +78,26 @@ def test_plan_geometry_invariants(weights_sn):
                 pix = grid_gather(b, np.arange(b["pixels"])[:, None], n)[..., 0]
                 assert pix.min() >= 0 and pix.max() < b["pixels"] and len(np.unique(pix)) == pix.size
     pe.close()
+
+
+def test_tiny_last_dense_keeps_precision(weights_sn):
+    """last_dense is zero-initialised in the reference and trained with lr 1e-3, so a real checkpoint may hold
+    weights around 1e-5 - below the fp16 normal range (6.1e-5).  The plan scales every output column by a power of
+    two before the fp16 cast and undoes it in the head epilogue, so the mask keeps its relative accuracy."""
+    w = dict(weights_sn)
+    w["last_dense/w"] = (w["last_dense/w"] * np.float32(1e-5 / np.abs(w["last_dense/w"]).max())).astype(np.float32)
+    w["last_dense/b"] = (w["last_dense/b"] * np.float32(1e-2)).astype(np.float32)
+    assert np.abs(w["last_dense/w"]).max() < 2e-5
+    pe = PlanExec(w, 0, win_cap=4, row_cap=1)
+    net = O.Net(w, 0)
+    lm = O.logmag_phase(O.normalise(synth.mixture(0.07, 4)[:400 + 160 * 3]))[0]            # 4 windows
+    rng = np.random.default_rng(3)
+    ea = rng.normal(0, 2, (1, 512)).astype(np.float32)
+    eb = rng.normal(0, 2, (1, 512)).astype(np.float32)
+    den = pe.masknet(lm, np.array([0, lm.shape[0]]), ea, eb)
+    with torch.no_grad():
+        win = torch.from_numpy(O.strided_crop(lm, 35))
+        ref = net.mask_net(win, torch.from_numpy(ea).expand(4, -1), torch.from_numpy(eb).expand(4, -1)).numpy()
+    assert np.abs(ref - lm).max() > 0                       # the head still contributes
+    assert _rel(den - lm, ref - lm) < 2e-3                  # a plain fp16 cast of 1e-5 weights loses ~2 decimal digits
+    pe.close()

@@ -36,7 +36,11 @@ def test_index_reader_on_reference_files():
     assert {k: [v["dtype"], list(v["shape"]), v["offset"], v["size"]] for k, v in e.items()} == idx
     with pytest.raises(FileNotFoundError):                           # the data shard is an LFS pointer
         W.load_bundle("/root/reference/N_HANS___Selective_Noise/trained_model/81448_0-1000000")
-    w, src = W.load_or_init(0, "/root/reference/N_HANS___Selective_Noise/trained_model")
+    # like the reference (SN/apply.py:428-432), a checkpoint that cannot be restored is an error ...
+    with pytest.raises(W.CheckpointMissing):
+        W.load_or_init(0, "/root/reference/N_HANS___Selective_Noise/trained_model", allow_random=False)
+    # ... unless random-init weights of the identical architecture are explicitly allowed
+    w, src = W.load_or_init(0, "/root/reference/N_HANS___Selective_Noise/trained_model", allow_random=True)
     assert src == "random-init" and len(w) == 571
 
 
