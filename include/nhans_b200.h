@@ -97,6 +97,12 @@ int nhans_enhance_batch(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_o
                         const int64_t* a_offs, const int16_t* ctx_b, const int64_t* b_offs, int16_t* out_i16,
                         float* out_f32, float* mixproc_f32);
 int nhans_sync(nhans_ctx* ctx);
+/* Consecutive nhans_enhance_batch calls are double buffered: the host-to-device copies of batch i + 1 and the
+ * device-to-host copies of batch i - 1 run on their own CUDA streams while batch i computes (SN/apply.py:440-450 is
+ * the loop this pipelines).  nhans_sync waits for everything; nhans_sync_previous waits only until the results of
+ * every batch but the most recently enqueued one are in host memory, so a caller can unpack batch i while batch
+ * i + 1 runs. */
+int nhans_sync_previous(nhans_ctx* ctx);
 
 /* The same path split at the PCIe boundary, for device-resident timing: upload stages a batch in HBM,
  * run processes the staged batch (no host traffic), download copies the results out. */

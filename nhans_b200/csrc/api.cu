@@ -77,6 +77,17 @@ struct ProfRec {
   double flops, bytes;
 };
 
+// Host <-> device staging of one batch.  There are two sets so that consecutive nhans_enhance_batch calls overlap:
+// the H2D copies of batch i + 1 and the D2H copies of batch i - 1 run on their own streams while batch i computes.
+struct IoSlot {
+  DBuf mix, a, b, d_mix_offs, d_a_offs, d_b_offs, d_frame_offs, d_out_offs, d_ctx_frame_offs;
+  DBuf out_i16, out_f32;
+  cudaEvent_t uploaded = nullptr;   // h2d stream: inputs of the batch staged in this set have landed
+  cudaEvent_t consumed = nullptr;   // compute stream: every kernel reading / writing this set has finished
+  cudaEvent_t drained = nullptr;    // d2h stream: outputs of this set have reached the host
+  bool d2h_pending = false;
+};
+
 struct Batch {
   int U = 0;
   bool has_a = false;
@@ -84,9 +95,10 @@ struct Batch {
   std::vector<long long> mix_offs, a_offs, b_offs, frame_offs, out_offs, ctx_frame_offs;
   long long total_frames = 0, total_out = 0;
   int max_frames = 0;
-  DBuf mix, a, b, d_mix_offs, d_a_offs, d_b_offs, d_frame_offs, d_out_offs, d_ctx_frame_offs;
+  IoSlot io[2];
+  int cur = 0;                      // set the staged / running batch uses
   DBuf peak_mix, peak_a, peak_b;
-  DBuf logmag, phase, den, ctxlm_a, ctxlm_b, emb_a, emb_b, cond, out_i16, out_f32, mixproc, removed, comp, sums, snr;
+  DBuf logmag, phase, den, ctxlm_a, ctxlm_b, emb_a, emb_b, cond, mixproc, removed, comp, sums, snr;
 };
 
 }  // namespace
@@ -95,7 +107,8 @@ struct nhans_ctx {
   int device = 0, variant = 0;
   int win_cap = 2048, row_cap = 32;
   int n_sm = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // compute
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::string err;
   std::string json;
   EncodeTiledFn encode = nullptr;
@@ -502,9 +515,9 @@ int check_kernel_flag(nhans_ctx* ctx) {
 
 int frames_of(long long n) { return n >= 400 ? (int)(1 + (n - 400) / 160) : 0; }
 
-int to_device_offs(nhans_ctx* ctx, DBuf& d, const std::vector<long long>& h) {
+int to_device_offs(nhans_ctx* ctx, DBuf& d, const std::vector<long long>& h, cudaStream_t stream = nullptr) {
   CK(d.ensure(h.size() * sizeof(long long)));
-  CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, stream ? stream : ctx->stream));
   return 0;
 }
 
@@ -555,6 +568,11 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   ctx->n_sm = prop.multiProcessorCount;
   auto bail = [&](const std::string& m) { g_create_error = m; return NHANS_ERR_CUDA; };
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if ((e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if ((e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  for (IoSlot& io : ctx->batch.io)
+    for (cudaEvent_t* ev : {&io.uploaded, &io.consumed, &io.drained})
+      if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess || !fn)
@@ -577,9 +595,16 @@ void nhans_destroy(nhans_ctx* ctx) {
   free_net(ctx->main_net);
   free_net(ctx->tower);
   Batch& b = ctx->batch;
-  for (DBuf* d : {&b.mix, &b.a, &b.b, &b.d_mix_offs, &b.d_a_offs, &b.d_b_offs, &b.d_frame_offs, &b.d_out_offs,
-                  &b.d_ctx_frame_offs, &b.peak_mix, &b.peak_a, &b.peak_b, &b.logmag, &b.phase, &b.den, &b.ctxlm_a,
-                  &b.ctxlm_b, &b.emb_a, &b.emb_b, &b.cond, &b.out_i16, &b.out_f32, &b.mixproc, &b.removed, &b.comp, &b.sums,
+  if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+  for (IoSlot& io : b.io) {
+    for (DBuf* d : {&io.mix, &io.a, &io.b, &io.d_mix_offs, &io.d_a_offs, &io.d_b_offs, &io.d_frame_offs, &io.d_out_offs,
+                    &io.d_ctx_frame_offs, &io.out_i16, &io.out_f32})
+      d->release();
+    for (cudaEvent_t ev : {io.uploaded, io.consumed, io.drained}) if (ev) cudaEventDestroy(ev);
+  }
+  for (DBuf* d : {&b.peak_mix, &b.peak_a, &b.peak_b, &b.logmag, &b.phase, &b.den, &b.ctxlm_a,
+                  &b.ctxlm_b, &b.emb_a, &b.emb_b, &b.cond, &b.mixproc, &b.removed, &b.comp, &b.sums,
                   &b.snr, &ctx->silent_emb})
     d->release();
   for (auto& t : ctx->tmp) t.release();
@@ -588,6 +613,8 @@ void nhans_destroy(nhans_ctx* ctx) {
   for (auto& ev : ctx->ev_pool) cudaEventDestroy(ev);
   if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   delete ctx;
 }
 
@@ -872,20 +899,26 @@ int nhans_upload(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, in
   for (int u = 0; u <= U; ++u) b.ctx_frame_offs[u] = (long long)u * kCtxFrames;
   b.total_frames = b.frame_offs[U];
   b.total_out = b.out_offs[U];
-  CK(b.mix.ensure(b.mix_offs[U] * 2 + 32));
-  CK(cudaMemcpyAsync(b.mix.p, mix + mix_offs[0], b.mix_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
-  CK(b.b.ensure(b.b_offs[U] * 2 + 32));
-  CK(cudaMemcpyAsync(b.b.p, ctx_b + b_offs[0], b.b_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
+  // stage into the set the previous batch does NOT use; its last user (two batches ago) must have finished
+  b.cur ^= 1;
+  IoSlot& io = b.io[b.cur];
+  cudaStream_t hs = ctx->h2d_stream;
+  CK(cudaStreamWaitEvent(hs, io.consumed, 0));
+  CK(io.mix.ensure(b.mix_offs[U] * 2 + 32));
+  CK(cudaMemcpyAsync(io.mix.p, mix + mix_offs[0], b.mix_offs[U] * 2, cudaMemcpyHostToDevice, hs));
+  CK(io.b.ensure(b.b_offs[U] * 2 + 32));
+  CK(cudaMemcpyAsync(io.b.p, ctx_b + b_offs[0], b.b_offs[U] * 2, cudaMemcpyHostToDevice, hs));
   if (b.has_a) {
-    CK(b.a.ensure(b.a_offs[U] * 2 + 32));
-    CK(cudaMemcpyAsync(b.a.p, ctx_a + a_offs[0], b.a_offs[U] * 2, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = to_device_offs(ctx, b.d_a_offs, b.a_offs))) return rc;
+    CK(io.a.ensure(b.a_offs[U] * 2 + 32));
+    CK(cudaMemcpyAsync(io.a.p, ctx_a + a_offs[0], b.a_offs[U] * 2, cudaMemcpyHostToDevice, hs));
+    if ((rc = to_device_offs(ctx, io.d_a_offs, b.a_offs, hs))) return rc;
   }
-  if ((rc = to_device_offs(ctx, b.d_mix_offs, b.mix_offs))) return rc;
-  if ((rc = to_device_offs(ctx, b.d_b_offs, b.b_offs))) return rc;
-  if ((rc = to_device_offs(ctx, b.d_frame_offs, b.frame_offs))) return rc;
-  if ((rc = to_device_offs(ctx, b.d_out_offs, b.out_offs))) return rc;
-  if ((rc = to_device_offs(ctx, b.d_ctx_frame_offs, b.ctx_frame_offs))) return rc;
+  if ((rc = to_device_offs(ctx, io.d_mix_offs, b.mix_offs, hs))) return rc;
+  if ((rc = to_device_offs(ctx, io.d_b_offs, b.b_offs, hs))) return rc;
+  if ((rc = to_device_offs(ctx, io.d_frame_offs, b.frame_offs, hs))) return rc;
+  if ((rc = to_device_offs(ctx, io.d_out_offs, b.out_offs, hs))) return rc;
+  if ((rc = to_device_offs(ctx, io.d_ctx_frame_offs, b.ctx_frame_offs, hs))) return rc;
+  CK(cudaEventRecord(io.uploaded, hs));
   b.staged = true;
   return NHANS_OK;
 }
@@ -909,23 +942,27 @@ int nhans_run(nhans_ctx* ctx) {
   CK(b.ctxlm_b.ensure(cbytes));
   CK(b.emb_b.ensure((size_t)U * 512 * 4));
   CK(b.cond.ensure((size_t)U * n_cols * 4));
-  CK(b.out_i16.ensure(b.total_out * 2 + 32));
-  CK(b.out_f32.ensure(b.total_out * 4 + 4));
+  IoSlot& io = b.io[b.cur];
+  CK(io.out_i16.ensure(b.total_out * 2 + 32));
+  CK(io.out_f32.ensure(b.total_out * 4 + 4));
   CK(b.mixproc.ensure(b.total_out * 4 + 4));
   if (!b.has_a && (rc = ensure_silent(ctx))) return rc;
 
+  // the inputs of this set have landed, and the outputs the set held two batches ago have reached the host
+  CK(cudaStreamWaitEvent(ctx->stream, io.uploaded, 0));
+  if (io.d2h_pending) CK(cudaStreamWaitEvent(ctx->stream, io.drained, 0));
   // front end: a2-a4 for the mixture and the first 200 frames of each context (SN/apply.py:359-387)
-  CK(launch_peaks(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), U, b.peak_mix.as<int>()));
-  CK(launch_peaks(ctx->stream, b.b.as<int16_t>(), b.d_b_offs.as<long long>(), U, b.peak_b.as<int>()));
+  CK(launch_peaks(ctx->stream, io.mix.as<int16_t>(), io.d_mix_offs.as<long long>(), U, b.peak_mix.as<int>()));
+  CK(launch_peaks(ctx->stream, io.b.as<int16_t>(), io.d_b_offs.as<long long>(), U, b.peak_b.as<int>()));
   ctx->launches += 2;
   {
     ProfScope ps(ctx, 1, 0, 2.0 * b.mix_offs[U] + 3.0 * sbytes);
-    CK(launch_stft(ctx->stream, b.mix.as<int16_t>(), b.d_mix_offs.as<long long>(), b.d_frame_offs.as<long long>(), U,
+    CK(launch_stft(ctx->stream, io.mix.as<int16_t>(), io.d_mix_offs.as<long long>(), io.d_frame_offs.as<long long>(), U,
                    b.peak_mix.as<int>(), b.max_frames, b.total_frames, b.logmag.as<float>(), b.phase.as<float>(), true));
   }
   {
     ProfScope ps(ctx, 4, 0, 0);
-    CK(launch_stft(ctx->stream, b.b.as<int16_t>(), b.d_b_offs.as<long long>(), b.d_ctx_frame_offs.as<long long>(), U,
+    CK(launch_stft(ctx->stream, io.b.as<int16_t>(), io.d_b_offs.as<long long>(), io.d_ctx_frame_offs.as<long long>(), U,
                    b.peak_b.as<int>(), kCtxFrames, (long long)U * kCtxFrames, b.ctxlm_b.as<float>(), nullptr));
   }
   const float* emb_a = nullptr;
@@ -933,10 +970,10 @@ int nhans_run(nhans_ctx* ctx) {
   if (b.has_a) {
     CK(b.ctxlm_a.ensure(cbytes));
     CK(b.emb_a.ensure((size_t)U * 512 * 4));
-    CK(launch_peaks(ctx->stream, b.a.as<int16_t>(), b.d_a_offs.as<long long>(), U, b.peak_a.as<int>()));
+    CK(launch_peaks(ctx->stream, io.a.as<int16_t>(), io.d_a_offs.as<long long>(), U, b.peak_a.as<int>()));
     ctx->launches += 1;
     ProfScope ps(ctx, 4, 0, 0);
-    CK(launch_stft(ctx->stream, b.a.as<int16_t>(), b.d_a_offs.as<long long>(), b.d_ctx_frame_offs.as<long long>(), U,
+    CK(launch_stft(ctx->stream, io.a.as<int16_t>(), io.d_a_offs.as<long long>(), io.d_ctx_frame_offs.as<long long>(), U,
                    b.peak_a.as<int>(), kCtxFrames, (long long)U * kCtxFrames, b.ctxlm_a.as<float>(), nullptr));
   }
   // embedding towers: once per distinct context clip, not once per window
@@ -953,15 +990,16 @@ int nhans_run(nhans_ctx* ctx) {
     CK(launch_cond_table(ctx->stream, emb_a, stride_a, b.emb_b.as<float>(), 512, U, ctx->main_net.Pa, ctx->main_net.Pb,
                          ctx->main_net.c, n_cols, b.cond.as<float>()));
   }
-  if ((rc = run_masknet(ctx, b.logmag.as<float>(), b.d_frame_offs.as<long long>(), b.frame_offs.data(), U, b.total_frames,
+  if ((rc = run_masknet(ctx, b.logmag.as<float>(), io.d_frame_offs.as<long long>(), b.frame_offs.data(), U, b.total_frames,
                         b.cond.as<float>(), b.den.as<float>())))
     return rc;
   {
     ProfScope ps(ctx, 2, 0, 3.0 * sbytes + 6.0 * b.total_out);
-    CK(launch_istft(ctx->stream, b.den.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
-                    b.d_out_offs.as<long long>(), U, b.peak_mix.as<int>(), 0, b.max_frames, b.out_f32.as<float>(),
-                    b.out_i16.as<int16_t>(), true));
+    CK(launch_istft(ctx->stream, b.den.as<float>(), b.phase.as<float>(), io.d_frame_offs.as<long long>(),
+                    io.d_out_offs.as<long long>(), U, b.peak_mix.as<int>(), 0, b.max_frames, io.out_f32.as<float>(),
+                    io.out_i16.as<int16_t>(), true));
   }
+  CK(cudaEventRecord(io.consumed, ctx->stream));
   b.done = true;
   return NHANS_OK;
 }
@@ -971,15 +1009,20 @@ int nhans_download(nhans_ctx* ctx, int16_t* out_i16, float* out_f32, float* mixp
   Batch& b = ctx->batch;
   if (!b.done) return fail(ctx, NHANS_ERR_STATE, "nhans_run has not produced a batch");
   CK(cudaSetDevice(ctx->device));
+  IoSlot& io = b.io[b.cur];
   if (mixproc_f32) {
     // 'mixed_processed.wav' (SN/apply.py:457-458): iSTFT of the window centres, i.e. of the input spectrogram
     ProfScope ps(ctx, 2, 0, 3.0 * b.total_frames * kBins * 4 + 4.0 * b.total_out);
-    CK(launch_istft(ctx->stream, b.logmag.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
-                    b.d_out_offs.as<long long>(), b.U, b.peak_mix.as<int>(), 0, b.max_frames, b.mixproc.as<float>(), nullptr, true));
+    CK(launch_istft(ctx->stream, b.logmag.as<float>(), b.phase.as<float>(), io.d_frame_offs.as<long long>(),
+                    io.d_out_offs.as<long long>(), b.U, b.peak_mix.as<int>(), 0, b.max_frames, b.mixproc.as<float>(), nullptr, true));
     CK(cudaMemcpyAsync(mixproc_f32, b.mixproc.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (out_i16) CK(cudaMemcpyAsync(out_i16, b.out_i16.p, b.total_out * 2, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_f32) CK(cudaMemcpyAsync(out_f32, b.out_f32.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // the outputs leave on their own stream, so that the next batch can start computing meanwhile
+  CK(cudaStreamWaitEvent(ctx->d2h_stream, io.consumed, 0));
+  if (out_i16) CK(cudaMemcpyAsync(out_i16, io.out_i16.p, b.total_out * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  if (out_f32) CK(cudaMemcpyAsync(out_f32, io.out_f32.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CK(cudaEventRecord(io.drained, ctx->d2h_stream));
+  io.d2h_pending = true;
   return NHANS_OK;
 }
 
@@ -989,19 +1032,20 @@ int nhans_postmix(nhans_ctx* ctx, float compensate, int ac, float* mixed_f32, fl
   Batch& b = ctx->batch;
   if (!b.done) return fail(ctx, NHANS_ERR_STATE, "nhans_run has not produced a batch");
   CK(cudaSetDevice(ctx->device));
+  IoSlot& io = b.io[b.cur];
   CK(b.removed.ensure(b.total_out * 4 + 4));
   CK(b.comp.ensure(b.total_out * 4 + 4));
   CK(b.sums.ensure(sizeof(double) * 2 * b.U));
   CK(b.snr.ensure(sizeof(float) * b.U));
   {
     ProfScope ps(ctx, 2, 0, 4.0 * b.total_frames * kBins * 4 + 12.0 * b.total_out);
-    CK(launch_istft_post(ctx->stream, b.den.as<float>(), b.logmag.as<float>(), b.phase.as<float>(), b.d_frame_offs.as<long long>(),
-                         b.d_out_offs.as<long long>(), b.U, b.max_frames, nullptr, b.mixproc.as<float>(), b.removed.as<float>(),
+    CK(launch_istft_post(ctx->stream, b.den.as<float>(), b.logmag.as<float>(), b.phase.as<float>(), io.d_frame_offs.as<long long>(),
+                         io.d_out_offs.as<long long>(), b.U, b.max_frames, nullptr, b.mixproc.as<float>(), b.removed.as<float>(),
                          b.sums.as<double>(), true));
   }
   {
     ProfScope ps(ctx, 4, 0, 0);
-    CK(launch_compensate(ctx->stream, b.out_f32.as<float>(), b.removed.as<float>(), b.d_out_offs.as<long long>(), b.U,
+    CK(launch_compensate(ctx->stream, io.out_f32.as<float>(), b.removed.as<float>(), io.d_out_offs.as<long long>(), b.U,
                          b.sums.as<double>(), compensate, ac, compensated_f32 ? b.comp.as<float>() : nullptr, b.snr.as<float>()));
   }
   if (mixed_f32) CK(cudaMemcpyAsync(mixed_f32, b.mixproc.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1024,9 +1068,28 @@ int nhans_sync(nhans_ctx* ctx) {
   if (!ctx) return NHANS_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e1 = cudaStreamSynchronize(ctx->h2d_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->d2h_stream);
+  for (IoSlot& io : ctx->batch.io) io.d2h_pending = false;
   int rc;
   if ((rc = check_kernel_flag(ctx))) return rc;
   CK(e);
+  CK(e1);
+  CK(e2);
+  return NHANS_OK;
+}
+
+int nhans_sync_previous(nhans_ctx* ctx) {
+  if (!ctx) return NHANS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  IoSlot& io = ctx->batch.io[ctx->batch.cur ^ 1];
+  if (io.d2h_pending) {
+    cudaError_t e = cudaEventSynchronize(io.drained);
+    io.d2h_pending = false;
+    int rc;
+    if ((rc = check_kernel_flag(ctx))) return rc;
+    CK(e);
+  }
   return NHANS_OK;
 }
 
@@ -1041,6 +1104,9 @@ void nhans_host_free(void* p) {
 int nhans_event_record(nhans_ctx* ctx, int slot) {
   if (!ctx || slot < 0 || slot >= 16) return NHANS_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  // the event orders after the copies of batches already enqueued, so that elapsed times cover them
+  for (IoSlot& io : ctx->batch.io)
+    if (io.d2h_pending) CK(cudaStreamWaitEvent(ctx->stream, io.drained, 0));
   CK(cudaEventRecord(ctx->events[slot], ctx->stream));
   return NHANS_OK;
 }

@@ -81,6 +81,10 @@ class Engine:
         if getattr(self, "h", None):
             self.lib.nhans_destroy(self.h)
             self.h = None
+            for pool in self.__dict__.get("_stage_bufs", []):
+                for buf in pool.values():
+                    buf.free()
+            self.__dict__.pop("_stage_bufs", None)
 
     def __del__(self):
         try:
@@ -266,25 +270,65 @@ class Engine:
         if sync:
             self.sync()
 
-    def enhance(self, mix_clips, ctx_a_clips, ctx_b_clips, want_f32=True, want_i16=True, want_mixproc=False):
-        """Lists of int16 clips -> dict of per-utterance outputs.  ctx_a_clips may be None (Silent.wav)."""
-        mix, mo = pack(mix_clips)
-        b, bo = pack(ctx_b_clips)
-        a, ao = pack(ctx_a_clips) if ctx_a_clips is not None else (None, None)
+    # Pinned staging: two sets of grow-only cudaHostAlloc buffers, one per batch the library keeps in flight
+    # (nhans_enhance_batch is double buffered), so every H2D / D2H copy is a true asynchronous DMA.
+    def _pinned(self, stage, key, n, dtype):
+        pool = self.__dict__.setdefault("_stage_bufs", [{}, {}])[stage]
+        cur = pool.get(key)
+        if cur is None or cur.array.size < n:
+            if cur is not None:
+                cur.free()
+            cur = PinnedArray((max(int(n * 1.25), 1024),), dtype)
+            pool[key] = cur
+        return cur.array[:n]
+
+    def _pack_pinned(self, stage, key, clips):
+        offs = np.zeros(len(clips) + 1, np.int64)
+        for i, c in enumerate(clips):
+            offs[i + 1] = offs[i] + len(c)
+        buf = self._pinned(stage, key, int(offs[-1]), np.int16)
+        for i, c in enumerate(clips):
+            buf[offs[i]:offs[i + 1]] = c
+        return buf, offs
+
+    def submit(self, mix_clips, ctx_a_clips, ctx_b_clips, want_f32=True, want_i16=True, want_mixproc=False):
+        """Stage a batch in pinned memory and enqueue H2D + kernels + D2H without waiting.  Up to two batches may be
+        in flight: collect() the older one before submitting a third.  -> ticket for collect()."""
+        stage = self.__dict__.get("_next_stage", 0)
+        busy = self.__dict__.setdefault("_stage_busy", [False, False])
+        if busy[stage]:
+            raise NhansError(-3, "two batches are already in flight: collect() one first")
+        mix, mo = self._pack_pinned(stage, "mix", mix_clips)
+        b, bo = self._pack_pinned(stage, "b", ctx_b_clips)
+        a, ao = self._pack_pinned(stage, "a", ctx_a_clips) if ctx_a_clips is not None else (None, None)
         oo = self.output_offsets(mo)
         n = int(oo[-1])
-        o16 = np.zeros(n, np.int16) if want_i16 else None
-        o32 = np.zeros(n, np.float32) if want_f32 else None
-        mp = np.zeros(n, np.float32) if want_mixproc else None
-        self.enhance_packed(mix, mo, a, ao, b, bo, o16, o32, mp)
+        o16 = self._pinned(stage, "o16", n, np.int16) if want_i16 else None
+        o32 = self._pinned(stage, "o32", n, np.float32) if want_f32 else None
+        mp = self._pinned(stage, "mp", n, np.float32) if want_mixproc else None
+        self.enhance_packed(mix, mo, a, ao, b, bo, o16, o32, mp, sync=False)
+        busy[stage] = True
+        self._next_stage = stage ^ 1
+        return dict(stage=stage, oo=oo, o16=o16, o32=o32, mp=mp)
+
+    def collect(self, ticket, newer_in_flight=False):
+        """Wait for a submitted batch and copy its outputs out of the staging buffers.  With newer_in_flight the wait
+        covers only this (older) batch, so the newer one keeps computing while the caller unpacks."""
+        if newer_in_flight:
+            self._ck(self.lib.nhans_sync_previous(self.h))
+        else:
+            self.sync()
+        oo = ticket["oo"]
         res = {"out_offs": oo}
-        if want_i16:
-            res["i16"] = unpack(o16, oo)
-        if want_f32:
-            res["f32"] = unpack(o32, oo)
-        if want_mixproc:
-            res["mixed_processed"] = unpack(mp, oo)
+        for key, name in (("o16", "i16"), ("o32", "f32"), ("mp", "mixed_processed")):
+            if ticket[key] is not None:
+                res[name] = [np.array(v) for v in unpack(ticket[key], oo)]      # copies: the staging buffer is reused
+        self._stage_busy[ticket["stage"]] = False
         return res
+
+    def enhance(self, mix_clips, ctx_a_clips, ctx_b_clips, want_f32=True, want_i16=True, want_mixproc=False):
+        """Lists of int16 clips -> dict of per-utterance outputs.  ctx_a_clips may be None (Silent.wav)."""
+        return self.collect(self.submit(mix_clips, ctx_a_clips, ctx_b_clips, want_f32, want_i16, want_mixproc))
 
     def postmix(self, out_offs, compensate=0.0, ac=False):
         """SN post-mix outputs of the batch just enhanced -> dict of per-utterance lists + snr_est array."""

@@ -1,10 +1,17 @@
 """Utterance sharding across the GPUs of one box (SURVEY.md §8 e): every utterance is independent in eval
-mode (batch-norm uses population statistics, N_HANS___Selective_Noise/blocks.py:104-108), so the batch is
-cut into contiguous blocks, one per GPU, each GPU holds a full weight replica and there is NO collective
-on the data path - only host scatter of int16 PCM and host gather of int16 PCM."""
+mode (batch-norm uses population statistics, N_HANS___Selective_Noise/blocks.py:104-108), so a batch is cut into
+chunks of utterances, each GPU holds a full weight replica and there is NO collective on the data path - only
+host scatter of int16 PCM and host gather of int16 PCM.
+
+Chunks are dealt DYNAMICALLY: every GPU has a host thread that pulls the next chunk from a shared queue as soon as
+it has room, so a GPU that runs slower under the power cap (round 1 measured 2.7 % between boxes) simply takes
+fewer chunks instead of holding the whole job back.  Each thread keeps two chunks in flight on its engine (pinned
+double-buffered staging + the library's copy streams): chunk i + 1 is packed and uploaded while chunk i computes,
+chunk i is unpacked while chunk i + 1 computes."""
 from __future__ import annotations
 
 import threading
+import time
 
 
 def shard_range(n_items, rank, world):
@@ -15,7 +22,7 @@ def shard_range(n_items, rank, world):
 
 
 def shard_by_load(lengths, world):
-    """Ragged batches: longest-first round-robin deal (balances frames per GPU). -> list of index lists."""
+    """Static deal for ragged batches: longest-first onto the least loaded GPU. -> list of index lists."""
     order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
     load = [0] * world
     out = [[] for _ in range(world)]
@@ -24,6 +31,29 @@ def shard_by_load(lengths, world):
         out[r].append(i)
         load[r] += lengths[i]
     return [sorted(s) for s in out]
+
+
+def make_chunks(lengths, chunk_utts):
+    """Work units of the dynamic deal: utterances sorted longest first (the long chunks go out first, the short ones
+    fill the tail) in groups of `chunk_utts`. -> list of index lists covering every utterance exactly once."""
+    order = sorted(range(len(lengths)), key=lambda i: (-lengths[i], i))
+    chunk_utts = max(1, int(chunk_utts))
+    return [sorted(order[k:k + chunk_utts]) for k in range(0, len(order), chunk_utts)]
+
+
+class ChunkQueue:
+    """Thread-safe dispenser of chunk indices."""
+
+    def __init__(self, n):
+        self.n, self.next, self.lock = n, 0, threading.Lock()
+
+    def take(self):
+        with self.lock:
+            if self.next >= self.n:
+                return None
+            k = self.next
+            self.next += 1
+            return k
 
 
 class MultiGpu:
@@ -36,24 +66,44 @@ class MultiGpu:
             e = Engine(d, variant, win_capacity, row_capacity)
             e.load_weights(weights)
             self.engines.append(e)
+        self.last_stats = None
 
-    def enhance(self, mix_clips, ctx_a_clips, ctx_b_clips, **kw):
+    def enhance(self, mix_clips, ctx_a_clips, ctx_b_clips, chunk_utts=64, **kw):
+        """Same result as Engine.enhance on one GPU (utterances are independent), gathered in input order.
+        self.last_stats holds per-GPU chunk counts, audio seconds and busy time of the call."""
         world = len(self.engines)
-        shards = shard_by_load([len(c) for c in mix_clips], world)
-        results = [None] * world
+        chunks = make_chunks([len(c) for c in mix_clips], chunk_utts)
+        queue = ChunkQueue(len(chunks))
+        done = [None] * len(chunks)
         errors = []
+        stats = [dict(device=e.device, chunks=0, utterances=0, samples=0, busy_s=0.0) for e in self.engines]
 
         def work(r):
-            idx = shards[r]
-            if not idx:
-                return
+            eng, st = self.engines[r], stats[r]
+            t0 = time.perf_counter()
+            prev = None                                   # (chunk index, ticket) in flight
             try:
-                results[r] = self.engines[r].enhance([mix_clips[i] for i in idx],
-                                                     None if ctx_a_clips is None else [ctx_a_clips[i] for i in idx],
-                                                     [ctx_b_clips[i] for i in idx], **kw)
+                while True:
+                    k = queue.take()
+                    cur = None
+                    if k is not None:
+                        idx = chunks[k]
+                        cur = (k, eng.submit([mix_clips[i] for i in idx],
+                                             None if ctx_a_clips is None else [ctx_a_clips[i] for i in idx],
+                                             [ctx_b_clips[i] for i in idx], **kw))
+                        st["chunks"] += 1
+                        st["utterances"] += len(idx)
+                        st["samples"] += sum(len(mix_clips[i]) for i in idx)
+                    if prev is not None:
+                        done[prev[0]] = eng.collect(prev[1], newer_in_flight=cur is not None)
+                    prev = cur
+                    if cur is None:
+                        break
             except Exception as ex:  # surfaced to the caller below
                 errors.append(ex)
+            st["busy_s"] = time.perf_counter() - t0
 
+        t_all = time.perf_counter()
         threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
         for t in threads:
             t.start()
@@ -62,15 +112,14 @@ class MultiGpu:
         if errors:
             raise errors[0]
         out = {}
-        for r, idx in enumerate(shards):
-            if not idx:
-                continue
-            for key, vals in results[r].items():
+        for k, idx in enumerate(chunks):
+            for key, vals in done[k].items():
                 if key == "out_offs":
                     continue
                 out.setdefault(key, [None] * len(mix_clips))
                 for j, i in enumerate(idx):
                     out[key][i] = vals[j]
+        self.last_stats = dict(wall_s=time.perf_counter() - t_all, chunk_utts=chunk_utts, n_chunks=len(chunks), per_gpu=stats)
         return out
 
     def close(self):

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nhans_b200.runtime import shard_by_load, shard_range
+from nhans_b200.runtime import ChunkQueue, MultiGpu, make_chunks, shard_by_load, shard_range
 
 
 def test_shard_range_partitions():
@@ -37,8 +37,11 @@ def _worker(rank, world, port, out):
     mine = torch.tensor([float(hi - lo)])
     tot = mine.clone()
     dist.all_reduce(tot)                                   # every utterance is owned exactly once
-    ms = torch.tensor([10.0 + rank])                       # bench.py: time = max over ranks
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = torch.tensor([10.0 + rank])                       # bench.py: time = max over ranks, every rank's time is reported
+    allv = [torch.zeros_like(ms) for _ in range(world)]
+    dist.all_gather(allv, ms)
+    assert [float(v) for v in allv] == [10.0 + r for r in range(world)]
+    ms = torch.tensor([max(float(v) for v in allv)])
     dist.barrier()
     if rank == 0:
         out.put((float(tot), float(ms)))
@@ -60,3 +63,52 @@ def test_gloo_world_size_2():
     assert all(p.exitcode == 0 for p in procs)
     tot, ms = q.get(timeout=10)
     assert tot == 101.0 and ms == 11.0
+
+
+def test_make_chunks_cover_everything_once():
+    rng = np.random.default_rng(1)
+    for n, c in ((0, 4), (1, 64), (10, 3), (257, 64), (8192, 64)):
+        lengths = rng.integers(400, 160000, n).tolist()
+        chunks = make_chunks(lengths, c)
+        assert sorted(i for ch in chunks for i in ch) == list(range(n))
+        assert all(1 <= len(ch) <= c for ch in chunks)
+        if n:
+            # longest utterances go out first
+            assert max(lengths) in [lengths[i] for i in chunks[0]]
+    q = ChunkQueue(3)
+    assert [q.take() for _ in range(5)] == [0, 1, 2, None, None]
+
+
+class _FakeEngine:
+    """Stands in for Engine in the dynamic deal: `delay` seconds of 'GPU time' per chunk."""
+
+    def __init__(self, device, delay):
+        self.device, self.delay, self.in_flight = device, delay, 0
+
+    def submit(self, mixes, a, b, **kw):
+        assert self.in_flight < 2                              # the library keeps at most two batches in flight
+        self.in_flight += 1
+        return dict(mixes=mixes, t=__import__("time").perf_counter())
+
+    def collect(self, ticket, newer_in_flight=False):
+        import time
+        time.sleep(self.delay)
+        self.in_flight -= 1
+        return {"out_offs": None, "i16": [np.asarray(m) * 2 for m in ticket["mixes"]]}
+
+    def close(self):
+        pass
+
+
+def test_dynamic_deal_follows_gpu_speed_and_keeps_order():
+    """A GPU that is 4x slower ends up with about a quarter of the chunks; results come back in input order."""
+    mg = MultiGpu.__new__(MultiGpu)
+    mg.engines = [_FakeEngine(0, 0.002), _FakeEngine(1, 0.008)]
+    mg.last_stats = None
+    rng = np.random.default_rng(2)
+    clips = [rng.integers(-100, 100, int(n)).astype(np.int16) for n in rng.integers(400, 2000, 300)]
+    out = mg.enhance(clips, None, clips, chunk_utts=5)
+    assert all(np.array_equal(out["i16"][i], clips[i] * 2) for i in range(300))
+    st = mg.last_stats["per_gpu"]
+    assert st[0]["chunks"] + st[1]["chunks"] == 60 and sum(s["utterances"] for s in st) == 300
+    assert st[0]["chunks"] > 2 * st[1]["chunks"]               # the fast engine pulled most of the queue
