@@ -65,10 +65,13 @@ struct NetDev {
   float *Pa = nullptr, *Pb = nullptr, *c = nullptr;
   int *u_frame = nullptr, *u_lo = nullptr, *u_hi = nullptr, *u_utt = nullptr;
   float* convC = nullptr;           // main net: per-frame first-convolution table (kernels.h FrameConvDev)
+  float* head_scratch = nullptr;    // main net: split-K partial sums of last_dense [kHeadSplit][capacity][208]
   long long crow_cap = 0;
   std::vector<void*> allocs;
   bool ready = false;
 };
+
+constexpr int kHeadSplit = 8;       // K splits of last_dense (13312 / 64 = 208 k-blocks -> 26 per split)
 
 struct ProfRec {
   int kind;
@@ -128,6 +131,7 @@ struct nhans_ctx {
   unsigned long long* debug_stats = nullptr;   // [128][8] per-layer wait-cycle counters (NHANS_DEBUG_STATS=1)
   int desc_mode = 0;
   bool use_walk = true;             // row-walk kernel for the 64-channel stage (NHANS_NO_WALK=1: plain N = 64 GEMM)
+  bool use_gen = true;              // resblock1_1_conv2 builds its A operand from the per-frame table (NHANS_NO_GEN=1: window_expand)
   double layer_acc[128][4] = {};
   double launches = 0;              // every kernel launched by this context (counted even when not profiling)
 };
@@ -204,6 +208,12 @@ int realise_net(nhans_ctx* ctx, NetDev& net) {
     CK(cudaMalloc(&p, (size_t)4 * net.crow_cap * kBins * 64 * sizeof(float)));
     net.allocs.push_back(p);
     net.convC = reinterpret_cast<float*>(p);
+  }
+  if (P.cond.n_cols > 0 && !P.gemm.empty() && P.gemm.back().epi.head && !getenv("NHANS_NO_SPLITK")) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)kHeadSplit * P.capacity * P.gemm.back().N * sizeof(float)));
+    net.allocs.push_back(p);
+    net.head_scratch = reinterpret_cast<float*>(p);
   }
   if ((rc = upload(ctx, net, P.first.w, &net.first_w))) return rc;
   if ((rc = upload(ctx, net, P.first.epi.bias, &net.first_bias))) return rc;
@@ -374,6 +384,8 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
             const PassInfo* pass = nullptr) {
   const NetPlan& P = net.plan;
   UnitTable ut{net.u_frame, net.u_lo, net.u_hi, net.u_utt};
+  bool gen_first = false;
+  long long gen_crow0 = 0;
   {
     const DirectLayer& D = P.first;
     DirectDev d;
@@ -405,8 +417,16 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
       if (f.rows <= net.crow_cap) {
         // (expanding the pass in slices so that a slice's table stays L2-resident was measured: no gain)
         CK(launch_frame_conv(ctx->stream, f));
-        CK(launch_window_expand(ctx->stream, d, net.convC, f.crow0, net.crow_cap, 0, units));
-        ctx->launches += 1;
+        // the row-walk kernel of the next layer builds its A operand from the table (conv_walk.cu kWalkGen); otherwise
+        // the table is expanded into the (window, row) activation tensor here
+        gen_first = ctx->use_walk && ctx->use_gen && !P.gemm.empty() && P.gemm[0].walk && net.layers[0].w_walk &&
+                    P.gemm[0].a_buf[0] == D.out.buf && D.epi.relu && d.epi.ttab16;
+        if (gen_first) {
+          gen_crow0 = f.crow0;
+        } else {
+          CK(launch_window_expand(ctx->stream, d, net.convC, f.crow0, net.crow_cap, 0, units));
+          ctx->launches += 1;
+        }
         done = true;
       }
     }
@@ -428,6 +448,10 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.epi.tab_H = L.Ho;
     g.epi.tab_W = L.epi.pair ? L.epi.pair_W : L.Wo;
     g.err_flag = ctx->err_flag_dev;
+    g.ksplit = 1;
+    // last_dense: 16 row tiles per 2048-window pass but K = 13312 - split K over the idle SMs (deterministic two-stage sum)
+    const bool split_head = L.epi.head && net.head_scratch && units >= 256 && (int)L.groups.size() % kHeadSplit == 0;
+    if (split_head) { g.ksplit = kHeadSplit; g.split_scratch = net.head_scratch; }
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
     g.debug_stats = ctx->debug_stats ? ctx->debug_stats + 8 * ((&net == &ctx->tower ? 64 : 0) + (int)i) : nullptr;
     ProfScope ps(ctx, 0, 2.0 * L.macs_per_unit * units, 0, (&net == &ctx->tower ? 64 : 0) + (int)i);
@@ -437,6 +461,10 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
       wd.plane_pitch = g.plane_pitch; wd.plane_rows = g.plane_rows;
       wd.H = L.Ho; wd.Wq = L.Wq; wd.Wo = L.Wo; wd.pt = L.c_pt; wd.pl = L.c_pl;
       wd.units = ut; wd.epi = g.epi; wd.err_flag = g.err_flag; wd.debug_stats = g.debug_stats;
+      if (i == 0 && gen_first) {
+        wd.gen_C = net.convC; wd.gen_crow0 = gen_crow0; wd.gen_crow_cap = net.crow_cap;
+        wd.gen_ttab16 = reinterpret_cast<const __half*>(net.first_ttab16);
+      }
       cudaError_t le = launch_walk(ctx->stream, ctx->n_sm, D.mapA0, D.mapBwalk, wd);
       if (le != cudaSuccess)
         return fail(ctx, NHANS_ERR_CUDA, "launch of row-walk layer " + L.name + ": " + cudaGetErrorString(le));
@@ -446,6 +474,10 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
       cudaError_t le = launch_gemm(ctx->stream, ctx->n_sm, D.mapA0, D.mapA1, D.mapB, D.mapBhalf, g, ctx->desc_mode);
       if (le != cudaSuccess)
         return fail(ctx, NHANS_ERR_CUDA, "launch of layer " + L.name + " (M " + std::to_string(g.M) + ", BN " + std::to_string(g.BN) + "): " + cudaGetErrorString(le));
+      if (split_head) {
+        CK(launch_head_reduce(ctx->stream, net.head_scratch, kHeadSplit, units, L.N, D.res_scale, D.bias, raw, net.u_frame, out_f32));
+        ctx->launches += 1;
+      }
     }
   }
   return 0;
@@ -562,6 +594,7 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   if (const char* dbg = getenv("NHANS_DEBUG_SKIP_EPILOGUE")) ctx->debug_skip_epilogue = atoi(dbg);
   if (const char* dbg = getenv("NHANS_DESC_MODE")) ctx->desc_mode = atoi(dbg);
   if (const char* dbg = getenv("NHANS_NO_WALK")) ctx->use_walk = atoi(dbg) == 0;
+  if (const char* dbg = getenv("NHANS_NO_GEN")) ctx->use_gen = atoi(dbg) == 0;
   if (const char* dbg = getenv("NHANS_DEBUG_STATS")) {
     if (atoi(dbg) && cudaMalloc((void**)&ctx->debug_stats, 128 * 8 * 8) == cudaSuccess) cudaMemset(ctx->debug_stats, 0, 128 * 8 * 8);
   }

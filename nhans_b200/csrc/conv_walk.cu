@@ -16,6 +16,9 @@
 // (walk_sched.h; checked on the host by tests/host/walk_sched_check.cc).
 //
 //   warp 8      producer: the resident weights once, then one A slab per (tile, input row)
+//   warps 10-13 (resblock1_1_conv2 only) build the A slabs themselves from the per-frame table of the first
+//               convolution - relu(C[variant][frame + row][x] + T1[row]) -> fp16, written with TMA's 128-byte swizzle -
+//               so the first activation tensor (1.8 GB written + read per 2048-window pass) never exists in HBM
 //   warp 9      MMA issuer: 16 K steps (4 column taps x 4 x K = 16) per input row over the sliding slot window
 //   warps 0-7   epilogue, row per thread (thread = TMEM lane = pixel): everything that does not depend on the
 //               image row - the conditioning bias of the pixel's utterance and the frequency embedding F[x] - is
@@ -41,13 +44,15 @@ constexpr int kBBytes = kWalkKW * kBTile;          // 128 KB resident
 constexpr int kCtrlBytes = 1024;
 constexpr int kMaxH = 40;
 constexpr int kTabBytes = kMaxH * 64 * 4 + 2 * 64 * 4;
-constexpr int kWalkThreads = 320;
-constexpr int kWarpA = 8, kWarpMma = 9;
+constexpr int kWalkThreads = 320;                  // 8 epilogue warps + producer + MMA issuer
+constexpr int kGenWarps = 4;                       // + slab generator warps (kWalkGen launches only)
+constexpr int kWarpA = 8, kWarpMma = 9, kWarpGen0 = 10;
 constexpr int kWalkSmem = 1024 + kNA * kSlabBytes + kBBytes + kCtrlBytes + kTabBytes;
 static_assert(kWalkSmem <= 227 * 1024, "shared memory budget");
 
 constexpr int kWalkRes = 1;                        // + res_scale[c] * x (identity residual)
 constexpr int kWalkR1 = 2;                         // + r1_vec[c] * raw spectrogram value (1x1 transform with Cin = 1)
+constexpr int kWalkGen = 4;                        // A slabs generated from the per-frame table of the first convolution
 
 struct __align__(8) WalkCtrl {
   uint64_t a_full[kNA], a_empty[kNA];
@@ -74,9 +79,9 @@ __device__ __forceinline__ void stg256(void* ptr, const uint4& a, const uint4& b
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(kWalkThreads, 1)
+__global__ void __launch_bounds__(kWalkThreads + ((EPI & 4) ? kGenWarps * 32 : 0), 1)
 conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const WalkDev p) {
-  constexpr bool kRes = (EPI & kWalkRes) != 0, kR1 = (EPI & kWalkR1) != 0;
+  constexpr bool kRes = (EPI & kWalkRes) != 0, kR1 = (EPI & kWalkR1) != 0, kGen = (EPI & kWalkGen) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -98,7 +103,8 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     s_r1[threadIdx.x] = kR1 ? e.r1_vec[threadIdx.x] : 0.f;
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kNA; ++s) { ptx::mbar_init(&ctrl->a_full[s], 1); ptx::mbar_init(&ctrl->a_empty[s], 1); }
+    // a_full: one TMA transaction arrival, or one arrival per generator warp
+    for (int s = 0; s < kNA; ++s) { ptx::mbar_init(&ctrl->a_full[s], kGen ? kGenWarps : 1); ptx::mbar_init(&ctrl->a_empty[s], 1); }
     ptx::mbar_init(&ctrl->b_full, 1);
     for (int s = 0; s < kWalkSlots; ++s) { ptx::mbar_init(&ctrl->tmem_full[s], 1); ptx::mbar_init(&ctrl->tmem_empty[s], 8); }
     ptx::fence_barrier_init();
@@ -122,18 +128,92 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
     __syncwarp();
     uint32_t slot = 0, phase = 0;
+    if (!kGen) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * 128 - p.pl;
+        for (int r = 0; r < H; ++r) {
+          ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&ctrl->a_full[slot], (uint32_t)kSlabBytes);
+            ptx::tma_load_2d(smem_a + (size_t)slot * kSlabBytes, &mapA, &ctrl->a_full[slot], 0, r * p.plane_pitch + m0);
+          }
+          __syncwarp();
+          if (++slot == (uint32_t)kNA) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (kGen && warp >= kWarpGen0) {
+    // ===================== slab generators (4 warps): the first convolution's output never goes to HBM =====================
+    // Slab row j is pixel m0 + j = (unit, x); a lane owns one 16-byte chunk (8 channels) of one row per iteration and
+    // writes it where TMA's 128-byte swizzle would have put it: chunk c of row j at j * 128 + ((c ^ (j & 7)) << 4).
+    // All table loads of a step are issued before the wait for the free slab, so L2 latency overlaps the MMAs.
+    constexpr int kIts = (kSlabRows + 4 * kGenWarps - 1) / (4 * kGenWarps);   // 9 rows per lane
+    const int gw = warp - kWarpGen0;
+    const int c8 = lane & 7, cg = c8 * 8;
+    const size_t vplane = (size_t)p.gen_crow_cap * 201 * 64;
+    const int n_units = p.plane_rows / p.Wq;
+    uint32_t slot = 0, phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = tile * 128 - p.pl;
+      // the 136 rows span at most two units
+      const int unitA = (m0 < 0 ? 0 : m0) / p.Wq;
+      const int xA = m0 - unitA * p.Wq;                                     // x of slab row 0 relative to unit A (may be -1)
+      long long crowA = -1, crowB = -1;
+      if (unitA < n_units) crowA = (long long)p.units.frame[unitA] + 34LL * p.units.utt[unitA] - p.gen_crow0;
+      if (unitA + 1 < n_units) crowB = (long long)p.units.frame[unitA + 1] + 34LL * p.units.utt[unitA + 1] - p.gen_crow0;
+      // per-lane source offsets of its rows (independent of the image row): -1 = zero row (margin / outside the pass)
+      long long src_off[kIts];
+#pragma unroll
+      for (int it = 0; it < kIts; ++it) {
+        const int j = it * (4 * kGenWarps) + gw * 4 + (lane >> 3);
+        int x = xA + j;
+        long long crow = crowA;
+        if (x >= p.Wq) { x -= p.Wq; crow = crowB; }
+        src_off[it] = (j < kSlabRows && x >= 0 && x < p.Wo && crow >= 0) ? (crow * 201 + x) * 64 + cg : -1;
+      }
       for (int r = 0; r < H; ++r) {
-        ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&ctrl->a_full[slot], (uint32_t)kSlabBytes);
-          ptx::tma_load_2d(smem_a + (size_t)slot * kSlabBytes, &mapA, &ctrl->a_full[slot], 0, r * p.plane_pitch + m0);
+        const int variant = r == 0 ? 1 : (r == H - 2 ? 2 : (r == H - 1 ? 3 : 0));
+        const float* plane = p.gen_C + (size_t)variant * vplane + (size_t)r * 201 * 64;
+        float4 va[kIts], vb[kIts];
+#pragma unroll
+        for (int it = 0; it < kIts; ++it) {
+          if (src_off[it] >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(plane + src_off[it]);
+            va[it] = __ldg(src);
+            vb[it] = __ldg(src + 1);
+          }
         }
+        float t8[8];
+        {
+          const uint4 tv = __ldg(reinterpret_cast<const uint4*>(p.gen_ttab16 + r * 64 + cg));
+          const __half2* th = reinterpret_cast<const __half2*>(&tv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(th[k]); t8[2 * k] = f.x; t8[2 * k + 1] = f.y; }
+        }
+        ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
+        uint8_t* slab = smem_a + (size_t)slot * kSlabBytes;
+#pragma unroll
+        for (int it = 0; it < kIts; ++it) {
+          const int j = it * (4 * kGenWarps) + gw * 4 + (lane >> 3);
+          if (j >= kSlabRows) continue;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (src_off[it] >= 0) {
+            const float4 a = va[it], b = vb[it];
+            o.x = pack_half2(fmaxf(a.x + t8[0], 0.f), fmaxf(a.y + t8[1], 0.f));
+            o.y = pack_half2(fmaxf(a.z + t8[2], 0.f), fmaxf(a.w + t8[3], 0.f));
+            o.z = pack_half2(fmaxf(b.x + t8[4], 0.f), fmaxf(b.y + t8[5], 0.f));
+            o.w = pack_half2(fmaxf(b.z + t8[6], 0.f), fmaxf(b.w + t8[7], 0.f));
+          }
+          *reinterpret_cast<uint4*>(slab + j * 128 + ((c8 ^ (j & 7)) << 4)) = o;
+        }
+        ptx::fence_proxy_async();                // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ctrl->a_full[slot]);
         if (++slot == (uint32_t)kNA) { slot = 0; phase ^= 1; }
       }
     }
+  } else if (warp >= kWarpGen0) {
+    // no generated operand: the two extra warps have nothing to do
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
     const uint32_t idesc0 = (1u << 4) | ((128u >> 4) << 24);                 // fp16 x fp16 -> fp32, M = 128; N added per segment
@@ -354,7 +434,7 @@ template <int EPI>
 cudaError_t launch_flavour(cudaStream_t s, int grid, const CUtensorMap& a, const CUtensorMap& b, const WalkDev& p) {
   cudaError_t e = cudaFuncSetAttribute(conv64_walk_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem);
   if (e != cudaSuccess) return e;
-  conv64_walk_kernel<EPI><<<grid, kWalkThreads, kWalkSmem, s>>>(a, b, p);
+  conv64_walk_kernel<EPI><<<grid, kWalkThreads + ((EPI & kWalkGen) ? kGenWarps * 32 : 0), kWalkSmem, s>>>(a, b, p);
   return cudaGetLastError();
 }
 
@@ -368,6 +448,11 @@ cudaError_t launch_walk(cudaStream_t s, int n_sm, const CUtensorMap& mapA, const
     return cudaErrorInvalidValue;
   const int tiles = (p.plane_rows + 127) / 128;
   const int grid = tiles < n_sm ? tiles : n_sm;
+  if (p.gen_C) {
+    // generated A operand: the layer after the first convolution (rank-1 transform epilogue, 'SAME' 4 x 4 geometry)
+    if (!e.r1_vec || e.res || !p.gen_ttab16 || p.pl != 1 || p.Wo != 201) return cudaErrorInvalidValue;
+    return launch_flavour<kWalkR1 | kWalkGen>(s, grid, mapA, mapB, p);
+  }
   if (e.res) return launch_flavour<kWalkRes>(s, grid, mapA, mapB, p);
   if (e.r1_vec) return launch_flavour<kWalkR1>(s, grid, mapA, mapB, p);
   return launch_flavour<0>(s, grid, mapA, mapB, p);

@@ -70,7 +70,7 @@ __global__ void peak_kernel(const int16_t* __restrict__ pcm, const long long* __
 
 // One spectrum value -> log-magnitude and phase (or unit phasor) of bin `o`.
 template <bool PHASOR>
-__device__ __forceinline__ void emit_bin(float re, float im, size_t o, float* __restrict__ logmag, float* __restrict__ phase) {
+__device__ __forceinline__ void emit_bin(float re, float im, int o, float* __restrict__ logmag, float* __restrict__ phase) {
   const float r2 = re * re + im * im;
   if (PHASOR) {
     const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
@@ -108,13 +108,24 @@ __device__ __forceinline__ void warp_pass_b(float2* __restrict__ z, int nfw, int
 // ((1, 0) where X = 0) instead of the angle - what the fused path keeps between the two transforms (SURVEY.md A.3:
 // no atan2 here, no sincos in the inverse).
 template <bool PHASOR>
-__global__ void __launch_bounds__(kSW * 32)
+#ifndef NHANS_STFT_MINB
+#define NHANS_STFT_MINB 6
+#endif
+__global__ void __launch_bounds__(kSW * 32, NHANS_STFT_MINB)
 stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const long long* __restrict__ offs,
             const long long* __restrict__ frame_offs, const int* __restrict__ peak, float* __restrict__ logmag,
             float* __restrict__ phase) {
-  __shared__ __align__(16) int16_t s_raw[kSpanF + 16];        // TMA landing zone: 16-byte aligned start and size
   __shared__ __align__(16) float s_x[kSpanF];
   __shared__ __align__(16) float2 s_z[kSW][kFW * 200];
+  // TMA landing zone of the int16 span (16-byte aligned start and size): the FFT buffers, which nobody touches
+  // before the samples are converted
+#ifdef NHANS_STFT_NOALIAS
+  __shared__ __align__(16) int16_t s_raw_buf[kSpanF + 16];
+  int16_t* s_raw = s_raw_buf;
+#else
+  int16_t* s_raw = reinterpret_cast<int16_t*>(&s_z[0][0]);
+  static_assert(sizeof(float2) * kSW * kFW * 200 >= (kSpanF + 16) * sizeof(int16_t), "raw span must fit the FFT buffers");
+#endif
   __shared__ __align__(8) uint64_t s_bar;
   const int u = blockIdx.y;
   const int T = (int)(frame_offs[u + 1] - frame_offs[u]);
@@ -152,8 +163,7 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
   float2* z = s_z[warp];
   const float* x0 = s_x + warp * kFW * kHop;
   // pass A on the windowed, even/odd-packed samples z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 25 m1 + m2
-  for (int t = lane; t < nfw * 25; t += 32) {
-    const int f = t / 25, m2 = t - f * 25;
+  for (int t = lane, f = lane >= 25, m2 = lane - 25 * f; t < nfw * 25; t += 32) {
     float2 v[8];
 #pragma unroll
     for (int m1 = 0; m1 < 8; ++m1) {
@@ -166,23 +176,28 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
     z[f * 200 + m2] = v[0];
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) z[f * 200 + k1 * 25 + m2] = cmul(v[k1], __ldg(&g_tw200[m2 * k1]));
+    m2 += 7; f += 1;                     // t + 32 = 25 (f + 1) + (m2 + 7)
+    if (m2 >= 25) { m2 -= 25; f += 1; }
   }
   __syncwarp();
   warp_pass_b<false>(z, nfw, lane);
   // bins k and 200 - k from Z[k], Z[200 - k]:  with E = (Z[k] + conj Z[200-k]) / 2, P = e^{-2 pi i k / 400} (Z[k] - conj Z[200-k]) / 2:
   //   X[k] = E - i P,   X[200 - k] = conj(E) - i conj(P)
   const long long row0 = frame_offs[u] + t0 + warp * kFW;
-  for (int i = lane; i < nfw * 101; i += 32) {
-    const int f = i / 101, k = i - f * 101;
+  float* lm_w = logmag + (size_t)row0 * kBinsD;                       // 32-bit offsets from the warp's first row
+  float* ph_w = phase ? phase + (size_t)row0 * kBinsD * (PHASOR ? 2 : 1) : nullptr;
+  for (int i = lane, f = 0, k = lane; i < nfw * 101; i += 32) {
     const float2 a = z[f * 200 + k];
     const float2 b = z[f * 200 + (k ? 200 - k : 0)];
     const float2 w = __ldg(&g_tw400[k]);
     const float ex = 0.5f * (a.x + b.x), ey = 0.5f * (a.y - b.y);
     const float ox = 0.5f * (a.x - b.x), oy = 0.5f * (a.y + b.y);
     const float px = w.x * ox - w.y * oy, py = w.x * oy + w.y * ox;
-    const size_t o = (size_t)(row0 + f) * kBinsD;
-    emit_bin<PHASOR>(ex + py, ey - px, o + k, logmag, phase);
-    if (k != 100) emit_bin<PHASOR>(ex - py, -ey - px, o + 200 - k, logmag, phase);
+    const int o = f * kBinsD;
+    emit_bin<PHASOR>(ex + py, ey - px, o + k, lm_w, ph_w);
+    if (k != 100) emit_bin<PHASOR>(ex - py, -ey - px, o + 200 - k, lm_w, ph_w);
+    k += 32;
+    if (k >= 101) { k -= 101; f += 1; }
   }
 }
 
@@ -209,13 +224,13 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
   const int t_first = fa + warp * kFW;
   // S[k] = exp(logmag) * phasor; Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]) and
   // Z[200 - k] from the same pair
-  for (int i = lane; i < kFW * 101; i += 32) {
-    const int f = i / 101, k = i - f * 101;
+  for (int i = lane, f = 0, k = lane; i < kFW * 101; i += 32) {
     const int t = t_first + f;
     float2 sk = make_float2(0.f, 0.f), sm = sk;
     if (t >= 0 && t < T) {
       const size_t o = (size_t)(row0 + t) * kBinsD;
-      const float ak = expf(logmag[o + k]), am = expf(logmag[o + 200 - k]);
+      // __expf: 2 ulp, i.e. ~1e-6 relative on |S| - far inside the 1e-5 absolute bound of the waveform tests
+      const float ak = __expf(logmag[o + k]), am = __expf(logmag[o + 200 - k]);
       if (PHASOR) {
         const float2 pk = reinterpret_cast<const float2*>(phase)[o + k], pm = reinterpret_cast<const float2*>(phase)[o + 200 - k];
         sk = make_float2(ak * pk.x, ak * pk.y);
@@ -234,11 +249,12 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
     const float wx = w.x * dx + w.y * dy, wy = w.x * dy - w.y * dx;          // conj(w) * d
     z[f * 200 + k] = make_float2(ex - wy, ey + wx);
     if (k > 0 && k < 100) z[f * 200 + 200 - k] = make_float2(ex + wy, wx - ey);
+    k += 32;
+    if (k >= 101) { k -= 101; f += 1; }
   }
   __syncwarp();
   // pass A in place: task (f, m2) reads and writes the slots 25 j + m2
-  for (int t = lane; t < kFW * 25; t += 32) {
-    const int f = t / 25, m2 = t - f * 25;
+  for (int t = lane, f = lane >= 25, m2 = lane - 25 * f; t < kFW * 25; t += 32) {
     float2 v[8];
 #pragma unroll
     for (int m1 = 0; m1 < 8; ++m1) v[m1] = z[f * 200 + 25 * m1 + m2];
@@ -246,15 +262,18 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
     z[f * 200 + m2] = v[0];
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) z[f * 200 + k1 * 25 + m2] = cmul(v[k1], cconj(__ldg(&g_tw200[m2 * k1])));
+    m2 += 7; f += 1;                     // t + 32 = 25 (f + 1) + (m2 + 7)
+    if (m2 >= 25) { m2 -= 25; f += 1; }
   }
   __syncwarp();
   warp_pass_b<true>(z, kFW, lane);
   // frames: y_f[2m] = Re z[m] / 400, y_f[2m+1] = Im z[m] / 400, times the synthesis window
-  for (int i = lane; i < kFW * 200; i += 32) {
-    const int f = i / 200, m = i - f * 200;
+  for (int i = lane, m = lane; i < kFW * 200; i += 32) {
     const float2 v = z[i];
     const float2 w = __ldg(reinterpret_cast<const float2*>(g_winv) + m);
     z[i] = make_float2(v.x * (1.0f / 400.0f) * w.x, v.y * (1.0f / 400.0f) * w.y);
+    m += 32;
+    if (m >= 200) m -= 200;
   }
   __syncthreads();
 }

@@ -86,11 +86,13 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   bool b_ready = false;                                             // resident weights have landed
   long long w_tmem = 0, w_a = 0, w_b = 0;
   const long long t_start = clock64();
+  const int gper = (num_groups + p.ksplit - 1) / p.ksplit;      // groups per K split (ksplit = 1: all of them)
   for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+    const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
     ptx::mbar_wait_timed(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2, &w_tmem);
     ptx::tc_fence_after();
-    for (int g = 0; g < num_groups; ++g) {
+    for (int g = g_lo; g < g_hi; ++g) {
       const int ntaps = ctrl->groups[g].ntaps;
       for (int i0 = 0; i0 < MT; i0 += IL) {
         uint32_t a_lo[IL], d_tm[IL];
@@ -110,7 +112,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
           ptx::tc_fence_after();
           const uint32_t sh = (uint32_t)ctrl->groups[g].shift[t] * 8;
           const uint32_t b_lo = b_base + bslot * b_step;
-          const uint32_t first = (uint32_t)((g | t) != 0);
+          const uint32_t first = (uint32_t)(g != g_lo || t != 0);
           if (ptx::elect_one()) {
             const uint64_t db = desc_hi | b_lo;
 #pragma unroll
@@ -199,14 +201,15 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
   };
   for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-    const int n0 = (tile % n_tiles) * p.BN;
+    const int tile_sp = tile / p.ksplit, split = tile - tile_sp * p.ksplit;
+    const int n0 = (tile_sp % n_tiles) * p.BN;
     if (p.debug_skip_epilogue == 1) {
       ptx::mbar_wait(&ctrl->tmem_full[acc], acc_phase, p.err_flag, 4);
       release_acc(acc);
       continue;
     }
     // tile -> (row chunk, image row) with the image row fastest (kernels.h GemmDev)
-    const int mtile = tile / n_tiles;
+    const int mtile = tile_sp / n_tiles;
     const int tchunk = mtile / p.Ho, ho = mtile - tchunk * p.Ho;
     const int local0 = tchunk * (MT * sub_rows) + (int)rank * 128;      // first row of this CTA within the plane
     const int tile_m0 = ho * p.plane_pitch + local0;
@@ -304,6 +307,12 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
           const int r = g * 8 + sub;
           const uint4 u = stage[r * 4 + ((jc ^ (r >> 1)) & 3)];
           float4 f = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+          if (kHead && p.ksplit > 1) {
+            // split-K: raw partial sums of this split, [split][unit][N]; o_out = unit * 201 + col0
+            const size_t unit = (o_out[g] - col0) / 201;
+            *reinterpret_cast<float4*>(p.split_scratch + ((size_t)split * (p.plane_rows / p.Wq) + unit) * p.N + col0 + c0) = f;
+            continue;
+          }
           if (kHead) {
             const int col = col0 + c0;
             const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
@@ -590,7 +599,7 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int n_tiles = p.N / p.BN;
   const int tile_rows = (MT * 128) << cta_shift;
   const int m_tiles = p.Ho * ((p.plane_rows + tile_rows - 1) / tile_rows);
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = m_tiles * n_tiles * p.ksplit;
   const int num_groups = p.num_groups;
 
   for (int i = threadIdx.x; i < num_groups; i += blockDim.x) ctrl->groups[i] = p.groups[i];
@@ -657,11 +666,13 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // ===================== A producer: one slab per (group, sub-tile) =====================
     // (whole warp runs the loop; one elected lane issues the TMA - keeps the control flow warp-uniform)
     uint32_t slot = 0, phase = 0;
+    const int gper = (num_groups + p.ksplit - 1) / p.ksplit;
     for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift) {
-      const int mtile = tile / n_tiles;
+      const int mtile = (tile / p.ksplit) / n_tiles;
       const int tchunk = mtile / p.Ho;
       const int m0 = (mtile - tchunk * p.Ho) * p.plane_pitch + tchunk * tile_rows + (int)rank * 128;
-      for (int g = 0; g < num_groups; ++g) {
+      const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
+      for (int g = g_lo; g < g_hi; ++g) {
         const int row_off = ctrl->groups[g].row_off, col = ctrl->groups[g].col, map = ctrl->groups[g].map;
         for (int i = 0; i < MT; ++i) {
           ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
@@ -695,9 +706,11 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     } else {
       uint32_t slot = 0, phase = 0;
+      const int gper = (num_groups + p.ksplit - 1) / p.ksplit;
       for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift) {
-        const int n0 = (tile % n_tiles) * p.BN + (int)rank * (p.BN >> 1) * cta_shift;
-        for (int g = 0; g < num_groups; ++g) {
+        const int n0 = ((tile / p.ksplit) % n_tiles) * p.BN + (int)rank * (p.BN >> 1) * cta_shift;
+        const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
+        for (int g = g_lo; g < g_hi; ++g) {
           const int ntaps = ctrl->groups[g].ntaps;
           for (int t = 0; t < ntaps; ++t) {
             const int bk = ctrl->groups[g].bk[t];
@@ -822,7 +835,8 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   if ((desc_mode >> 1) & 7) { cfg.il = (desc_mode >> 1) & 7; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
   if (cfg.nb < 4) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight
   const int tile_rows = (cfg.mt * 128) << cta2;
-  const int tiles = p.Ho * ((p.plane_rows + tile_rows - 1) / tile_rows) * (p.N / p.BN);
+  if (p.ksplit < 1 || (p.ksplit > 1 && (!p.epi.head || !p.split_scratch || cfg.resident))) return cudaErrorInvalidValue;
+  const int tiles = p.Ho * ((p.plane_rows + tile_rows - 1) / tile_rows) * (p.N / p.BN) * p.ksplit;
   int grid = tiles < (n_sm >> cta2) ? tiles : (n_sm >> cta2);
   grid <<= cta2;                              // CTA pairs: two CTAs per tile
   const EpiDev& e = p.epi;

@@ -75,6 +75,11 @@ struct GemmDev {
   int Hq, Wq, Ho, Wo;
   UnitTable units;
   EpiDev epi;
+  // split-K (head only: last_dense has 16 row tiles but K = 13312): tile -> (tile / ksplit, split = tile % ksplit),
+  // split s accumulates the groups [s * gper, (s + 1) * gper) and stores its raw fp32 partial sums at
+  // split_scratch[s][unit][N]; head_reduce_kernel adds them in a fixed order (deterministic) and applies the epilogue
+  int ksplit;
+  float* split_scratch;
   int* err_flag;
   int debug_skip_epilogue;  // measurement aid: epilogue warps only release the accumulator
   unsigned long long* debug_stats;   // optional [8] cycle counters (wait times per role), or null
@@ -90,6 +95,12 @@ struct WalkDev {
   EpiDev epi;
   int* err_flag;
   unsigned long long* debug_stats;
+  // Generated A operand (resblock1_1_conv2 only): instead of reading the first convolution's output from HBM, two
+  // producer warps build every slab from the per-frame table of that convolution (FrameConvDev::C):
+  // A[unit, r, x, :] = relu(C[variant(r)][frame(unit) + 34 utt(unit) - crow0 + r][x][:] + T1[r][:]) in fp16
+  const float* gen_C;       // null: A comes from mapA (TMA)
+  long long gen_crow0, gen_crow_cap;
+  const __half* gen_ttab16; // [H][64] time embedding of the first convolution
 };
 
 struct DirectDev {
@@ -143,6 +154,9 @@ cudaError_t launch_cond_table(cudaStream_t s, const float* emb_a, int stride_a, 
                               const float* Pb, const float* c, int n_cols, float* out);
 // emb[n][c] = mean over `pixels` rows of act[n][pixels][C]
 cudaError_t launch_mean_pool(cudaStream_t s, const __half* act, int units, int pixels, int C, float* emb);
+// out[n][c] = (sum_s scratch[s][n][c]) * scale[c] + bias[c] + raw[frame[n]][c], c < 201 (head of main.py:238-242)
+cudaError_t launch_head_reduce(cudaStream_t s, const float* scratch, int ksplit, int units, int N, const float* scale, const float* bias,
+                               const float* raw, const int* frame, float* out);
 cudaError_t launch_units_main(cudaStream_t s, const long long* frame_offs, int U, int w0, int nwin, int* frame, int* lo,
                               int* hi, int* utt);
 cudaError_t launch_units_rows(cudaStream_t s, int r0, int n, int rows_per_unit, int* frame, int* lo, int* hi, int* utt);

@@ -430,6 +430,21 @@ __global__ void mean_pool_kernel(const __half* __restrict__ act, int pixels, int
   }
 }
 
+// Second stage of the split-K head (kernels.h GemmDev::ksplit): partial sums are added in split order, so the result
+// does not depend on which CTA finished first.
+__global__ void head_reduce_kernel(const float* __restrict__ scratch, int ksplit, int units, int N, const float* __restrict__ scale,
+                                   const float* __restrict__ bias, const float* __restrict__ raw, const int* __restrict__ frame,
+                                   float* __restrict__ out) {
+  const int n = blockIdx.x;
+  const size_t plane = (size_t)units * N;
+  const float* raw_row = raw + (size_t)frame[n] * 201;
+  for (int c = threadIdx.x; c < 201; c += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < ksplit; ++s) acc += scratch[s * plane + (size_t)n * N + c];
+    out[(size_t)n * 201 + c] = acc * scale[c] + bias[c] + raw_row[c];
+  }
+}
+
 // Window n of the chunk is global frame w0 + n (one window per STFT frame, SN/apply.py:378); its clip is
 // found by binary search in frame_offs.
 __global__ void units_main_kernel(const long long* __restrict__ frame_offs, int U, int w0, int nwin, int* frame, int* lo,
@@ -505,6 +520,13 @@ cudaError_t launch_cond_table(cudaStream_t s, const float* emb_a, int stride_a, 
 cudaError_t launch_mean_pool(cudaStream_t s, const __half* act, int units, int pixels, int C, float* emb) {
   if (units <= 0) return cudaSuccess;
   mean_pool_kernel<<<units, 256, 0, s>>>(act, pixels, C, emb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_reduce(cudaStream_t s, const float* scratch, int ksplit, int units, int N, const float* scale, const float* bias,
+                               const float* raw, const int* frame, float* out) {
+  if (units <= 0) return cudaSuccess;
+  head_reduce_kernel<<<units, 224, 0, s>>>(scratch, ksplit, units, N, scale, bias, raw, frame, out);
   return cudaGetLastError();
 }
 

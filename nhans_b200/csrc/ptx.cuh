@@ -65,12 +65,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug must not hang the GPU box, so after ~2 s the kernel records where it
 // was stuck and traps (the host sees a launch failure instead of a hang).
+#ifndef NHANS_WAIT_TIMEOUT_NS
+#define NHANS_WAIT_TIMEOUT_NS 2000000000ull          // the compute-sanitizer build raises it (kernels run ~100x slower)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = globaltimer();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer() - t0 > 2000000000ull) {
+    if ((++spins & 0x3ff) == 0 && globaltimer() - t0 > NHANS_WAIT_TIMEOUT_NS) {
       if (err_flag) atomicExch(err_flag, tag);
       __threadfence_system();
       __trap();

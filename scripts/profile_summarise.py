@@ -1,6 +1,6 @@
 """Turn the CSV exports of scripts/profile_capture.sh (gpurun_out/TAG_*.csv) into the committed summaries under
-profiles/ (launch shares, per-layer tensor / memory metrics, DSP kernels) and refresh profiles/gemm_traffic.json,
-which bench.py reads for roofline.traffic.  Usage: python scripts/profile_summarise.py TAG OUTPREFIX "note"."""
+profiles/ (launch shares, per-layer tensor / memory metrics, DSP kernels) and write profiles/r02_traffic.json, which
+bench.py reads for roofline.traffic.  Usage: python scripts/profile_summarise.py TAG OUTPREFIX "note"."""
 import csv
 import json
 import os
@@ -24,30 +24,29 @@ def short(name):
 
 
 # ---- launch list (long format: one row per launch x metric) ----
-r = rows_of(os.path.join(G, tag + "_launches.csv"))
-hdr = r[0]
-ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-tot = {}
-for row in r[1:]:
-    v = float(row[vi].replace(",", ""))
-    ms = v / 1e6 if row[ui] in ("ns", "nsecond") else v / 1e3 if row[ui] in ("us", "usecond") else v
-    k = short(row[ki])
-    a = tot.setdefault(k, [0, 0.0])
-    a[0] += 1
-    a[1] += ms
-allms = sum(a[1] for a in tot.values())
-with open(os.path.join(P, outp + "_launches_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv: python bench.py --steps 1 --warmup 1 --utts 32 --no-cpu-baseline (%s)\n" % note)
-    for k, a in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        f.write("%-40s launches=%4d total_ms=%9.3f share=%5.1f%%\n" % (k, a[0], a[1], 100 * a[1] / allms))
-with open(os.path.join(P, outp + "_launches.csv"), "w") as f:
-    f.write(open(os.path.join(G, tag + "_launches.csv")).read())
+lp = os.path.join(G, tag + "_launches.csv")
+if os.path.exists(lp):
+    r = rows_of(lp)
+    hdr = r[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    tot = {}
+    for row in r[1:]:
+        v = float(row[vi].replace(",", ""))
+        ms = v / 1e6 if row[ui] in ("ns", "nsecond") else v / 1e3 if row[ui] in ("us", "usecond") else v
+        a = tot.setdefault(short(row[ki]), [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    allms = sum(a[1] for a in tot.values())
+    with open(os.path.join(P, outp + "_launches_summary.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv: python bench.py --steps 1 --warmup 1 --utts 32 --no-cpu-baseline (%s)\n" % note)
+        for k, a in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-40s launches=%4d total_ms=%9.3f share=%5.1f%%\n" % (k, a[0], a[1], 100 * a[1] / allms))
+    with open(os.path.join(P, outp + "_launches.csv"), "w") as f:
+        f.write(open(lp).read())
 
-# ---- full capture of the GEMM layers (wide format) ----
-LAYERS = ["last_dense (prev pass)", "resblock1_1_conv2", "resblock1_2_conv1", "resblock1_2_conv2", "resblock2_1_conv1",
-          "resblock2_1_conv2", "resblock2_2_conv1", "resblock2_2_conv2", "resblock3_1_conv1", "resblock3_1_conv2",
-          "resblock3_2_conv1", "resblock3_2_conv2", "resblock4_1_conv1", "resblock4_1_conv2", "resblock4_2_conv1",
-          "resblock4_2_conv2", "last_conv"]
+LAYERS = ["resblock1_1_conv2", "resblock1_2_conv1", "resblock1_2_conv2", "resblock2_1_conv1", "resblock2_1_conv2", "resblock2_2_conv1",
+          "resblock2_2_conv2", "resblock3_1_conv1", "resblock3_1_conv2", "resblock3_2_conv1", "resblock3_2_conv2", "resblock4_1_conv1",
+          "resblock4_1_conv2", "resblock4_2_conv1", "resblock4_2_conv2", "last_conv", "last_dense"]
 COLS = ["launch__grid_size", "launch__cluster_size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
@@ -58,8 +57,7 @@ COLS = ["launch__grid_size", "launch__cluster_size", "gpu__time_duration.sum", "
 
 def wide(path):
     r = rows_of(path)
-    hdr, units = r[0], r[1]
-    return hdr, units, r[2:]
+    return r[0], r[1], r[2:]
 
 
 def cols(hdr, name):
@@ -87,14 +85,17 @@ def to_unit(v, u, want):
     return v
 
 
-gp = os.path.join(G, tag + "_gemm_raw.csv")
+gp = os.path.join(G, tag + "_tc_raw.csv")
 if os.path.exists(gp):
     hdr, units, rows = wide(gp)
     idx = [cols(hdr, c) for c in COLS]
-    with open(os.path.join(P, outp + "_gemm_ncu_full.txt"), "w") as f:
-        f.write("ncu --set full --clock-control none -k regex:gemm_shift -s 30 -c 17 (%s; one 2048-window pass of 32 x 4 s); exported with --page raw --csv on the GPU box\n" % note)
-        f.write("columns: " + ", ".join(COLS) + "  [time ms, dram GB]\n")
-        per = {}
+    ki = hdr.index("Kernel Name")
+    cmd = ("ncu --set full --clock-control none -k regex:gemm_shift|conv64_walk -s 31 -c 17 python bench.py --steps 1 --warmup 1 "
+           "--utts 32 --no-cpu-baseline (%s; one 2048-window pass)" % note)
+    per_kernel = {}
+    with open(os.path.join(P, outp + "_tc_ncu_full.txt"), "w") as f:
+        f.write(cmd + "; exported with --page raw --csv on the GPU box\n")
+        f.write("columns: kernel, " + ", ".join(COLS) + "  [time ms, dram GB]\n")
         for n, row in enumerate(rows):
             name = LAYERS[n] if n < len(LAYERS) else "launch %d" % n
             vals = []
@@ -105,26 +106,29 @@ if os.path.exists(gp):
                     continue
                 want = "ms" if "time_duration" in c else "GB" if "bytes" in c else ""
                 vals.append(to_unit(row[i], units[i], want))
-            f.write("%-24s" % name + "".join("%12.4f" % v for v in vals) + "\n")
+            kern = short(row[ki])
+            f.write("%-20s %-20s" % (name, kern) + "".join("%12.4f" % v for v in vals) + "\n")
             if name.startswith("resblock"):
-                per[name] = vals[3] + vals[4]
-    if per:
-        json.dump({"dram_bytes_per_launch": 1e9 * sum(per.values()) / len(per),
-                   "note": "mean over the 15 conv layers of one 2048-window pass (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum), " + note,
-                   "per_layer_GB": per}, open(os.path.join(P, "gemm_traffic.json"), "w"), indent=1)
-    with open(os.path.join(P, outp + "_gemm_ncu_raw.csv"), "w") as f:
+                per_kernel.setdefault(kern, {})[name] = vals[3] + vals[4]
+    out = {"command": cmd, "kernels": {}}
+    for kern, per in per_kernel.items():
+        out["kernels"][kern] = {"dram_bytes_per_launch": 1e9 * sum(per.values()) / len(per), "launches_averaged": len(per),
+                                "per_layer_GB": per}
+    json.dump(out, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
+    with open(os.path.join(P, outp + "_tc_ncu_raw.csv"), "w") as f:
         f.write(open(gp).read())
 
 dp = os.path.join(G, tag + "_dsp_raw.csv")
 if os.path.exists(dp):
     hdr, units, rows = wide(dp)
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-            "sm__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__registers_per_thread"]
+            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__grid_size", "launch__block_size", "launch__registers_per_thread"]
     ki = hdr.index("Kernel Name")
     with open(os.path.join(P, outp + "_dsp_ncu.txt"), "w") as f:
-        f.write("ncu --set full -k regex:stft_kernel|istft_kernel -c 8: bench.py --utts 256 (256 x 4 s; %s)\n" % note)
+        f.write("ncu --set full --clock-control none -k regex:stft_kernel|istft_kernel -c 8: bench.py --steps 1 --warmup 1 --utts 256 (256 x 4 s; %s)\n" % note)
         for row in rows:
-            parts = [short(row[ki])]
+            parts = [short(row[ki]) + ("<phasor>" if "<1>" in row[ki] or "<(bool)1>" in row[ki] else "")]
             for w in want:
                 i = pick(row, cols(hdr, w))
                 if i >= 0:

@@ -34,7 +34,7 @@ def test_embedding_tower(engine_sn, weights_sn, oracle_sn):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-def test_masknet_layers_and_output(variant, engine_sn, engine_ss, weights_sn, weights_ss, oracle_sn, oracle_ss):
+def test_masknet_layers_and_output(variant, engine_sn, engine_ss, weights_sn, weights_ss, oracle_sn, oracle_ss, monkeypatch):
     eng = engine_sn if variant == 0 else engine_ss
     w = weights_sn if variant == 0 else weights_ss
     net = oracle_sn if variant == 0 else oracle_ss
@@ -51,10 +51,26 @@ def test_masknet_layers_and_output(variant, engine_sn, engine_ss, weights_sn, we
     assert _rel(den - lm, den_pe - lm) < 2e-3 and np.abs(den - den_pe).max() < 2e-3
     plan = eng.plan(0)
     assert plan["bufs"] == pe.plan(0)["bufs"]
+    first_buf = plan["first"]["out"]["buf"]
     for g in plan["bufs"]:                                   # every activation grid, every logical pixel
         a = grid_gather(g, eng.read_buffer(0, g["buf"]).astype(np.float32), 9)
         b = grid_gather(g, pe.read_buffer(0, g["buf"]), 9)
+        if g["buf"] == first_buf and not a.any():
+            continue    # never materialised: resblock1_1_conv2 builds its operand from the per-frame table (conv_walk.cu kWalkGen)
         assert _rel(a, b) < 1e-3, g
+    # the first convolution's output itself: the same engine path with the operand generator switched off
+    monkeypatch.setenv("NHANS_NO_GEN", "1")
+    from nhans_b200.engine import Engine
+    nogen = Engine(0, variant, win_capacity=256, row_capacity=4)
+    try:
+        nogen.load_weights(w)
+        den2 = nogen.masknet(lm, fo, ea, eb)
+        g = plan["bufs"][first_buf]
+        a = grid_gather(g, nogen.read_buffer(0, first_buf).astype(np.float32), 9)
+        assert a.any() and _rel(a, grid_gather(g, pe.read_buffer(0, first_buf), 9)) < 1e-3
+        assert np.abs(den2 - den).max() < 2e-3               # generated operand == materialised operand (fp16 rounding of the same values)
+    finally:
+        nogen.close()
     pe.close()
     ref = []
     with torch.no_grad():
@@ -97,11 +113,13 @@ def test_row_walk_matches_plain_gemm(engine_sn, weights_sn, monkeypatch):
     assert sum(g["walk"] for g in engine_sn.plan(0)["gemm"]) == 3
     den = engine_sn.masknet(lm, fo, ea, eb)
     monkeypatch.setenv("NHANS_NO_WALK", "1")
+    monkeypatch.setenv("NHANS_NO_SPLITK", "1")                        # and last_dense as one K loop instead of 8 splits + reduce
     plain = Engine(0, 0, win_capacity=256, row_capacity=4)
     try:
         plain.load_weights(weights_sn)
         den_p = plain.masknet(lm, fo, ea, eb)
         assert np.abs(den - den_p).max() < 2e-3
+        assert np.isfinite(den).all()                                  # (the first pass, 256 windows, takes the split-K head)
         for g in engine_sn.plan(0)["gemm"]:
             if not g["walk"]:
                 continue

@@ -54,7 +54,7 @@ def test_mask_error_elementwise(variant, engine_sn, engine_ss, oracle_sn, oracle
     assert d.max() < 2.5e-3
 
 
-def test_fused_path_spectra_vs_oracle(engine_sn):
+def test_fused_path_spectra_vs_oracle(engine_sn, capsys):
     """The fused path does not call the bit-exact stage entries: it multiplies by the float64 reciprocal of the peak,
     takes log(|X|) through rsqrt and stores unit phasors.  Read those arrays back and compare them with the oracle."""
     mixes = [synth.mixture(0.8, 11), synth.mixture(0.33, 12)]
@@ -70,8 +70,17 @@ def test_fused_path_spectra_vs_oracle(engine_sn):
         rl, rp = O.logmag_phase(x[:O.trim_len(len(x))])
         g = lm[r0:r0 + T[u]]
         assert g.shape == rl.shape
-        assert np.abs(g - rl).max() < 1e-3                        # |d log-magnitude| = relative magnitude error
         mag = np.exp(rl.astype(np.float64))
+        d = np.abs(g - rl)                                        # |d log-magnitude| = relative magnitude error
+        # fp32 FFT-400: the absolute error of a bin is ~1e-6 of the frame's largest bin, so the 1e-3 RELATIVE bound can
+        # only hold for bins above ~1e-3 of that maximum (the reference's own fp32 FFT has the same floor); weaker bins
+        # are held to the absolute form of the same bound
+        strong = mag >= 1e-3 * mag.max(axis=1, keepdims=True)
+        with capsys.disabled():
+            print("\n[parity] fused spectra clip %d: |d logmag| max %.3e (bins >= 1e-3 of the frame max: %.3e, %d weaker bins)"
+                  % (u, d.max(), d[strong].max(), int((~strong).sum())))
+        assert d[strong].max() < 1e-3
+        assert (np.abs(np.exp(g.astype(np.float64)) - mag) / mag.max(axis=1, keepdims=True)).max() < 1e-5
         want = np.exp(1j * rp.astype(np.float64))
         got = ph[r0:r0 + T[u], :, 0].astype(np.float64) + 1j * ph[r0:r0 + T[u], :, 1]
         assert np.abs(np.abs(got) - 1.0).max() < 1e-5             # unit modulus
