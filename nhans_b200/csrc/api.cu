@@ -450,7 +450,9 @@ int run_net(nhans_ctx* ctx, NetDev& net, int units, const float* raw, const floa
     g.err_flag = ctx->err_flag_dev;
     g.ksplit = 1;
     // last_dense: 16 row tiles per 2048-window pass but K = 13312 - split K over the idle SMs (deterministic two-stage sum)
-    const bool split_head = L.epi.head && net.head_scratch && units >= 256 && (int)L.groups.size() % kHeadSplit == 0;
+    // (whatever the pass size: the summation order - and with it every output bit - must not depend on how many windows
+    // share the pass)
+    const bool split_head = L.epi.head && net.head_scratch && (int)L.groups.size() % kHeadSplit == 0;
     if (split_head) { g.ksplit = kHeadSplit; g.split_scratch = net.head_scratch; }
     g.debug_skip_epilogue = ctx->debug_skip_epilogue;
     g.debug_stats = ctx->debug_stats ? ctx->debug_stats + 8 * ((&net == &ctx->tower ? 64 : 0) + (int)i) : nullptr;

@@ -82,38 +82,41 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   const uint64_t desc_hi = ptx::umma_desc_sw128(0, 0);             // everything but the address field
   const uint32_t a_base = ptx::smem_u32(smem_a) >> 4, b_base = ptx::smem_u32(smem_b) >> 4;
   const uint32_t b_step = (uint32_t)b_bytes >> 4;
-  uint32_t aslot = 0, aphase = 0, bslot0 = 0, bphase0 = 0, it = 0;
-  bool b_ready = false;                                             // resident weights have landed
-  long long w_tmem = 0, w_a = 0, w_b = 0;
-  const long long t_start = clock64();
   const int gper = (num_groups + p.ksplit - 1) / p.ksplit;      // groups per K split (ksplit = 1: all of them)
-  for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
-    const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-    const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
-    ptx::mbar_wait_timed(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2, &w_tmem);
-    ptx::tc_fence_after();
-    for (int g = g_lo; g < g_hi; ++g) {
-      const int ntaps = ctrl->groups[g].ntaps;
-      for (int i0 = 0; i0 < MT; i0 += IL) {
-        uint32_t a_lo[IL], d_tm[IL];
+  // ONE elected lane runs the whole role - barrier waits, MMAs, commits.  Electing per tap (round 1) cost an
+  // elect / branch / warp-sync and a register -> uniform-register shuffle of every descriptor per 4-8 MMAs; in the
+  // row-walk kernel the same change was worth 20 %.
+  if (ptx::elect_one()) {
+    uint32_t aslot = 0, aphase = 0, bslot0 = 0, bphase0 = 0, it = 0;
+    bool b_ready = false;                                             // resident weights have landed
+    long long w_tmem = 0, w_a = 0, w_b = 0;
+    const long long t_start = clock64();
+    for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
+      ptx::mbar_wait_timed(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2, &w_tmem);
+      ptx::tc_fence_after();
+      for (int g = g_lo; g < g_hi; ++g) {
+        const int ntaps = ctrl->groups[g].ntaps;
+        for (int i0 = 0; i0 < MT; i0 += IL) {
+          uint32_t a_lo[IL], d_tm[IL];
 #pragma unroll
-        for (int ii = 0; ii < IL; ++ii) {
-          uint32_t sl = aslot + ii, ph = aphase;
-          if (sl >= (uint32_t)cfg.na) { sl -= cfg.na; ph ^= 1; }
-          ptx::mbar_wait_timed(&ctrl->a_full[sl], ph, p.err_flag, 3, &w_a);
-          a_lo[ii] = a_base + sl * (kSlabBytes >> 4);
-          d_tm[ii] = tmem_base + acc * 256 + (i0 + ii) * p.BN;
-        }
-        uint32_t bslot = bslot0, bphase = bphase0;
-        for (int t = 0; t < ntaps; ++t) {
-          if (cfg.resident) bslot = (uint32_t)ctrl->groups[g].bk[t];
-          if ((i0 == 0 && !cfg.resident) || (cfg.resident && !b_ready))
-            ptx::mbar_wait_timed(&ctrl->b_full[bslot], cfg.resident ? 0u : bphase, p.err_flag, 6, &w_b);
-          ptx::tc_fence_after();
-          const uint32_t sh = (uint32_t)ctrl->groups[g].shift[t] * 8;
-          const uint32_t b_lo = b_base + bslot * b_step;
-          const uint32_t first = (uint32_t)(g != g_lo || t != 0);
-          if (ptx::elect_one()) {
+          for (int ii = 0; ii < IL; ++ii) {
+            uint32_t sl = aslot + ii, ph = aphase;
+            if (sl >= (uint32_t)cfg.na) { sl -= cfg.na; ph ^= 1; }
+            ptx::mbar_wait_timed(&ctrl->a_full[sl], ph, p.err_flag, 3, &w_a);
+            a_lo[ii] = a_base + sl * (kSlabBytes >> 4);
+            d_tm[ii] = tmem_base + acc * 256 + (i0 + ii) * p.BN;
+          }
+          uint32_t bslot = bslot0, bphase = bphase0;
+          for (int t = 0; t < ntaps; ++t) {
+            if (cfg.resident) bslot = (uint32_t)ctrl->groups[g].bk[t];
+            if ((i0 == 0 && !cfg.resident) || (cfg.resident && !b_ready))
+              ptx::mbar_wait_timed(&ctrl->b_full[bslot], cfg.resident ? 0u : bphase, p.err_flag, 6, &w_b);
+            ptx::tc_fence_after();
+            const uint32_t sh = (uint32_t)ctrl->groups[g].shift[t] * 8;
+            const uint32_t b_lo = b_base + bslot * b_step;
+            const uint32_t first = (uint32_t)(g != g_lo || t != 0);
             const uint64_t db = desc_hi | b_lo;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                         // +32 B inside the swizzle atom per K = 16
@@ -126,29 +129,27 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
             if (i0 + IL >= MT && !cfg.resident) {
               if (CTA2) ptx::umma_commit_2sm(&ctrl->b_empty[bslot]); else ptx::umma_commit(&ctrl->b_empty[bslot]);
             }
+            if (!cfg.resident && ++bslot == (uint32_t)cfg.nb) { bslot = 0; bphase ^= 1; }
           }
-          __syncwarp();
-          if (!cfg.resident && ++bslot == (uint32_t)cfg.nb) { bslot = 0; bphase ^= 1; }
-        }
 #pragma unroll
-        for (int ii = 0; ii < IL; ++ii) {
-          if (ptx::elect_one()) { if (CTA2) ptx::umma_commit_2sm(&ctrl->a_empty[aslot]); else ptx::umma_commit(&ctrl->a_empty[aslot]); }
-          __syncwarp();
-          if (++aslot == (uint32_t)cfg.na) { aslot = 0; aphase ^= 1; }
+          for (int ii = 0; ii < IL; ++ii) {
+            if (CTA2) ptx::umma_commit_2sm(&ctrl->a_empty[aslot]); else ptx::umma_commit(&ctrl->a_empty[aslot]);
+            if (++aslot == (uint32_t)cfg.na) { aslot = 0; aphase ^= 1; }
+          }
+          if (i0 + IL >= MT) { bslot0 = bslot; bphase0 = bphase; }
         }
-        if (i0 + IL >= MT) { bslot0 = bslot; bphase0 = bphase; }
       }
+      b_ready = true;
+      if (CTA2) ptx::umma_commit_2sm(&ctrl->tmem_full[acc]); else ptx::umma_commit(&ctrl->tmem_full[acc]);
     }
-    b_ready = true;
-    if (ptx::elect_one()) { if (CTA2) ptx::umma_commit_2sm(&ctrl->tmem_full[acc]); else ptx::umma_commit(&ctrl->tmem_full[acc]); }
-    __syncwarp();
+    if (p.debug_stats) {
+      atomicAdd(p.debug_stats + 0, (unsigned long long)w_tmem);
+      atomicAdd(p.debug_stats + 1, (unsigned long long)w_a);
+      atomicAdd(p.debug_stats + 2, (unsigned long long)w_b);
+      atomicAdd(p.debug_stats + 4, (unsigned long long)(clock64() - t_start));
+    }
   }
-  if (p.debug_stats && (threadIdx.x & 31) == 0) {
-    atomicAdd(p.debug_stats + 0, (unsigned long long)w_tmem);
-    atomicAdd(p.debug_stats + 1, (unsigned long long)w_a);
-    atomicAdd(p.debug_stats + 2, (unsigned long long)w_b);
-    atomicAdd(p.debug_stats + 4, (unsigned long long)(clock64() - t_start));
-  }
+  __syncwarp();
 }
 
 // Epilogue flavours (compile-time: the epilogue is instruction bound, every runtime flag costs issue slots)

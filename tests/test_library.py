@@ -28,8 +28,17 @@ def test_sass_is_blackwell_native():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.SO_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):       # tcgen05.mma, TMA load, tcgen05.ld
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP"):       # tcgen05.mma, TMA tensor load, tcgen05.ld, 1-D bulk copy
         assert mnemonic in sass, mnemonic
+    # per kernel: both tensor-core kernels issue tcgen05.mma and read TMEM; the STFT kernel stages its samples with a bulk copy
+    funcs = re.split(r"Function : ", sass)
+    def has(kernel, mnemonic):
+        return any(kernel in f.split("\n", 1)[0] and mnemonic in f for f in funcs)
+    assert has("gemm_shift_kernel", "UTCHMMA") and has("gemm_shift_kernel", ".2CTA") and has("gemm_shift_kernel", "LDTM")
+    assert has("conv64_walk_kernel", "UTCHMMA") and has("conv64_walk_kernel", "UTMALDG") and has("conv64_walk_kernel", "LDTM")
+    assert has("stft_kernel", "UBLKCP")
+    # the committed table is generated from the same disassembly (scripts/sass_table.py)
+    assert os.path.exists(os.path.join(ROOT, "profiles", "r02_sass_table.txt"))
 
 
 def test_no_cpu_fallback():
