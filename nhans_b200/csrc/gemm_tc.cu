@@ -88,6 +88,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   // row-walk kernel the same change was worth 20 %.
   if (ptx::elect_one()) {
     uint32_t aslot = 0, aphase = 0, bslot0 = 0, bphase0 = 0, it = 0;
+    uint32_t full_par = 0;                                            // parity of b_full[s] as a group barrier, one bit per slot
     bool b_ready = false;                                             // resident weights have landed
     long long w_tmem = 0, w_a = 0, w_b = 0;
     const long long t_start = clock64();
@@ -98,21 +99,27 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
       ptx::tc_fence_after();
       for (int g = g_lo; g < g_hi; ++g) {
         const int ntaps = ctrl->groups[g].ntaps;
+        // the MT slabs of a group land on the barrier of the group's first slab (MT divides the ring depth, so a
+        // group never wraps): one wait per group
+        ptx::mbar_wait_timed(&ctrl->a_full[aslot], aphase, p.err_flag, 3, &w_a);
         for (int i0 = 0; i0 < MT; i0 += IL) {
           uint32_t a_lo[IL], d_tm[IL];
 #pragma unroll
           for (int ii = 0; ii < IL; ++ii) {
-            uint32_t sl = aslot + ii, ph = aphase;
-            if (sl >= (uint32_t)cfg.na) { sl -= cfg.na; ph ^= 1; }
-            ptx::mbar_wait_timed(&ctrl->a_full[sl], ph, p.err_flag, 3, &w_a);
-            a_lo[ii] = a_base + sl * (kSlabBytes >> 4);
+            a_lo[ii] = a_base + (aslot + ii) * (kSlabBytes >> 4);
             d_tm[ii] = tmem_base + acc * 256 + (i0 + ii) * p.BN;
           }
           uint32_t bslot = bslot0, bphase = bphase0;
+          if (i0 == 0 && !cfg.resident) {
+            // every B tile of the group lands on the barrier of the group's first slot: one wait per group
+            ptx::mbar_wait_timed(&ctrl->b_full[bslot0], (full_par >> bslot0) & 1u, p.err_flag, 6, &w_b);
+            full_par ^= 1u << bslot0;
+          }
           for (int t = 0; t < ntaps; ++t) {
-            if (cfg.resident) bslot = (uint32_t)ctrl->groups[g].bk[t];
-            if ((i0 == 0 && !cfg.resident) || (cfg.resident && !b_ready))
-              ptx::mbar_wait_timed(&ctrl->b_full[bslot], cfg.resident ? 0u : bphase, p.err_flag, 6, &w_b);
+            if (cfg.resident) {
+              bslot = (uint32_t)ctrl->groups[g].bk[t];
+              if (!b_ready) ptx::mbar_wait_timed(&ctrl->b_full[bslot], 0u, p.err_flag, 6, &w_b);
+            }
             ptx::tc_fence_after();
             const uint32_t sh = (uint32_t)ctrl->groups[g].shift[t] * 8;
             const uint32_t b_lo = b_base + bslot * b_step;
@@ -675,17 +682,18 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
       for (int g = g_lo; g < g_hi; ++g) {
         const int row_off = ctrl->groups[g].row_off, col = ctrl->groups[g].col, map = ctrl->groups[g].map;
+        uint64_t* gbar = &ctrl->a_full[slot];               // the group's slabs complete on its first slab's barrier
         for (int i = 0; i < MT; ++i) {
           ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
           if (ptx::elect_one()) {
             if (CTA2) {
               // both CTAs' slabs are credited to the leader's barrier
-              if (rank == 0) ptx::mbar_expect_tx(&ctrl->a_full[slot], 2 * kSlabBytes);
-              ptx::tma_load_2d_2sm(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, &ctrl->a_full[slot], col,
+              if (rank == 0 && i == 0) ptx::mbar_expect_tx(gbar, 2 * MT * kSlabBytes);
+              ptx::tma_load_2d_2sm(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, gbar, col,
                                    m0 + i * 256 + row_off);
             } else {
-              ptx::mbar_expect_tx(&ctrl->a_full[slot], kSlabBytes);
-              ptx::tma_load_2d(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, &ctrl->a_full[slot], col,
+              if (i == 0) ptx::mbar_expect_tx(gbar, MT * kSlabBytes);
+              ptx::tma_load_2d(smem_a + (size_t)slot * kSlabBytes, map ? &mapA1 : &mapA0, gbar, col,
                                m0 + i * 128 + row_off);
             }
           }
@@ -713,16 +721,18 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
         for (int g = g_lo; g < g_hi; ++g) {
           const int ntaps = ctrl->groups[g].ntaps;
+          // all B tiles of a group complete on the barrier of the group's first slot (one wait per group in the issuer)
+          uint64_t* gbar = &ctrl->b_full[slot];
           for (int t = 0; t < ntaps; ++t) {
             const int bk = ctrl->groups[g].bk[t];
             ptx::mbar_wait(&ctrl->b_empty[slot], phase ^ 1, p.err_flag, 5);
             if (ptx::elect_one()) {
               if (CTA2) {
-                if (rank == 0) ptx::mbar_expect_tx(&ctrl->b_full[slot], 2u * (uint32_t)b_bytes);
-                ptx::tma_load_2d_2sm(smem_b + (size_t)slot * b_bytes, &mapB, &ctrl->b_full[slot], bk * 64, n0);
+                if (rank == 0 && t == 0) ptx::mbar_expect_tx(gbar, 2u * (uint32_t)(ntaps * b_bytes));
+                ptx::tma_load_2d_2sm(smem_b + (size_t)slot * b_bytes, &mapB, gbar, bk * 64, n0);
               } else {
-                ptx::mbar_expect_tx(&ctrl->b_full[slot], (uint32_t)b_bytes);
-                ptx::tma_load_2d(smem_b + (size_t)slot * b_bytes, &mapB, &ctrl->b_full[slot], bk * 64, n0);
+                if (t == 0) ptx::mbar_expect_tx(gbar, (uint32_t)(ntaps * b_bytes));
+                ptx::tma_load_2d(smem_b + (size_t)slot * b_bytes, &mapB, gbar, bk * 64, n0);
               }
             }
             __syncwarp();
@@ -834,7 +844,7 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
   if ((desc_mode >> 1) & 7) { cfg.il = (desc_mode >> 1) & 7; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
-  if (cfg.nb < 4) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight
+  if (cfg.nb < 4 || cfg.na % cfg.mt != 0) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight; its slabs never wrap the A ring
   const int tile_rows = (cfg.mt * 128) << cta2;
   if (p.ksplit < 1 || (p.ksplit > 1 && (!p.epi.head || !p.split_scratch || cfg.resident))) return cudaErrorInvalidValue;
   const int tiles = p.Ho * ((p.plane_rows + tile_rows - 1) / tile_rows) * (p.N / p.BN) * p.ksplit;
