@@ -775,7 +775,13 @@ int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, int row, GemmCf
   // flavour's tab_bytes (padded tables + per-channel vectors) is computed by the caller and always taken
   c.tab_bytes = ((BN <= 128 || row) && tab_bytes > 0) ? ((tab_bytes + 127) & ~127) : 0;
   c.mt = 256 / BN < 1 ? 1 : 256 / BN;
-  c.na = 4;
+  // A ring: 4 slabs = 4 groups ahead for BN = 256 (one slab per group).  BN <= 128 tiles take two slabs per group and
+  // the stride-2 layers consume a group in ~1000 cycles, less than a TMA round trip: 6 slabs (3 groups ahead) cut the
+  // issuer's a_full stalls there (B tiles are 8 KB in these layers, the B ring stays >= 9 deep)
+  static const int na_env = getenv("NHANS_NA") ? atoi(getenv("NHANS_NA")) : 0;
+  c.na = BN <= 128 ? 6 : 4;
+  if (na_env > 0 && na_env <= kMaxA && na_env % c.mt == 0) c.na = na_env;
+  if (c.na % c.mt != 0) c.na = 4;
   const int epi_bytes = row ? 0 : kEpiBytes;
   const int budget = kSmemLimit - 1024 - kCtrlBytes - epi_bytes - c.tab_bytes - c.na * kSlabBytes;
   c.nb = budget / b_bytes;
