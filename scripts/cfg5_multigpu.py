@@ -22,7 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=8)
 ap.add_argument("--utts", type=int, default=8192)
 ap.add_argument("--seconds", type=float, default=10.0)
-ap.add_argument("--chunk", type=int, default=64)
+ap.add_argument("--chunk", type=int, default=32)
 ap.add_argument("--repeat", type=int, default=2)
 ap.add_argument("--check", type=int, default=6, help="utterances compared bit for bit with a single-engine run")
 a = ap.parse_args()

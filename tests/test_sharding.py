@@ -112,3 +112,23 @@ def test_dynamic_deal_follows_gpu_speed_and_keeps_order():
     st = mg.last_stats["per_gpu"]
     assert st[0]["chunks"] + st[1]["chunks"] == 60 and sum(s["utterances"] for s in st) == 300
     assert st[0]["chunks"] > 2 * st[1]["chunks"]               # the fast engine pulled most of the queue
+
+
+def test_pass_aware_chunks_fill_whole_passes():
+    """Chunks are closed where their windows nearly fill a whole number of 2048-window passes."""
+    from nhans_b200.runtime import frames_of
+    lengths = [160000] * 8192                                   # BASELINE config 5: 998 windows per clip
+    chunks = make_chunks(lengths, 32, pass_windows=2048)
+    assert sorted(i for ch in chunks for i in ch) == list(range(8192))
+    waste = []
+    for ch in chunks[:-1]:
+        w = sum(frames_of(lengths[i]) for i in ch)
+        passes = -(-w // 2048)
+        waste.append(1.0 - w / (passes * 2048.0))
+        assert 16 <= len(ch) <= 48
+    assert max(waste) < 0.05 and sum(waste) / len(waste) < 0.03
+    assert len(chunks) >= 8 * 20                                # fine enough for the dynamic deal on 8 GPUs
+    rng = np.random.default_rng(3)
+    ragged = rng.integers(8000, 200000, 500).tolist()
+    ch = make_chunks(ragged, 16, pass_windows=2048)
+    assert sorted(i for c in ch for i in c) == list(range(500))
