@@ -16,7 +16,7 @@
 // (walk_sched.h; checked on the host by tests/host/walk_sched_check.cc).
 //
 //   warp 8      producer: the resident weights once, then one A slab per (tile, input row)
-//   warps 10-13 (resblock1_1_conv2 only) build the A slabs themselves from the per-frame table of the first
+//   warps 10-15 (resblock1_1_conv2 only) build the A slabs themselves from the per-frame table of the first
 //               convolution - relu(C[variant][frame + row][x] + T1[row]) -> fp16, written with TMA's 128-byte swizzle -
 //               so the first activation tensor (1.8 GB written + read per 2048-window pass) never exists in HBM
 //   warp 9      MMA issuer: 16 K steps (4 column taps x 4 x K = 16) per input row over the sliding slot window
@@ -45,7 +45,7 @@ constexpr int kCtrlBytes = 1024;
 constexpr int kMaxH = 40;
 constexpr int kTabBytes = kMaxH * 64 * 4 + 2 * 64 * 4;
 constexpr int kWalkThreads = 320;                  // 8 epilogue warps + producer + MMA issuer
-constexpr int kGenWarps = 4;                       // + slab generator warps (kWalkGen launches only)
+constexpr int kGenWarps = 6;                       // + slab generator warps (kWalkGen launches only; 512 threads x 128 registers)
 constexpr int kWarpA = 8, kWarpMma = 9, kWarpGen0 = 10;
 constexpr int kWalkSmem = 1024 + kNA * kSlabBytes + kBBytes + kCtrlBytes + kTabBytes;
 static_assert(kWalkSmem <= 227 * 1024, "shared memory budget");
@@ -143,11 +143,11 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (kGen && warp >= kWarpGen0) {
-    // ===================== slab generators (4 warps): the first convolution's output never goes to HBM =====================
+    // ===================== slab generators (6 warps): the first convolution's output never goes to HBM =====================
     // Slab row j is pixel m0 + j = (unit, x); a lane owns one 16-byte chunk (8 channels) of one row per iteration and
     // writes it where TMA's 128-byte swizzle would have put it: chunk c of row j at j * 128 + ((c ^ (j & 7)) << 4).
     // All table loads of a step are issued before the wait for the free slab, so L2 latency overlaps the MMAs.
-    constexpr int kIts = (kSlabRows + 4 * kGenWarps - 1) / (4 * kGenWarps);   // 9 rows per lane
+    constexpr int kIts = (kSlabRows + 4 * kGenWarps - 1) / (4 * kGenWarps);   // rows per lane
     const int gw = warp - kWarpGen0;
     const int c8 = lane & 7, cg = c8 * 8;
     const size_t vplane = (size_t)p.gen_crow_cap * 201 * 64;
