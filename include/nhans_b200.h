@@ -149,6 +149,11 @@ int nhans_debug_read_buffer(nhans_ctx* ctx, int net, int buf, uint16_t* out, int
  * the oracle's SN/apply.py:368-375 arrays): which 0 = log-magnitude [frames][201], 1 = unit phasors X / |X|
  * [frames][201][2] (the fused path stores phasors instead of angles), 2 = denoised log-magnitude [frames][201]. */
 int nhans_debug_read_batch(nhans_ctx* ctx, int which, float* out, int64_t n_floats);
+/* Debug (NHANS_DEBUG_TIMELINE=1 at create time): device timestamps of the last batches that went through
+ * nhans_enhance_batch, in ms since the first one - out_ms[6 i + {0..5}] = H2D begin / end (copy-in stream), compute
+ * begin / end, D2H begin / end (copy-out stream); -1 where a stage did not run.  Returns the number of batches written.
+ * Synchronises the context. */
+int nhans_debug_timeline(nhans_ctx* ctx, double* out_ms, int max_batches);
 /* Debug: accumulated wait cycles of one tensor-core layer (needs NHANS_DEBUG_STATS=1 at create time):
  * {MMA waits accumulator free, MMA waits A, MMA waits B, epilogue waits accumulator ready, MMA warp total, ...}. */
 int nhans_debug_layer_stats(nhans_ctx* ctx, int net, int layer, uint64_t* out8);

@@ -17,7 +17,7 @@ SYMBOLS = [
     "nhans_upload", "nhans_run", "nhans_download", "nhans_postmix", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
     "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset",
     "nhans_profile_get_layer", "nhans_plan_json",
-    "nhans_debug_read_buffer", "nhans_debug_read_batch", "nhans_debug_layer_stats", "nhans_device_info",
+    "nhans_debug_read_buffer", "nhans_debug_read_batch", "nhans_debug_timeline", "nhans_debug_layer_stats", "nhans_device_info",
 ]
 
 
@@ -76,6 +76,7 @@ def load():
     lib.nhans_profile_get_layer.argtypes = [vp, i32, i32, vp]
     lib.nhans_debug_read_buffer.argtypes = [vp, i32, i32, vp, i64]
     lib.nhans_debug_read_batch.argtypes = [vp, i32, vp, i64]
+    lib.nhans_debug_timeline.argtypes = [vp, vp, i32]
     lib.nhans_device_info.argtypes = [vp, c.POINTER(i32), c.POINTER(i32), c.POINTER(i32), c.POINTER(i64)]
     _lib = lib
     return lib

@@ -5,6 +5,7 @@
 #include "../../include/nhans_b200.h"
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -130,6 +131,10 @@ struct nhans_ctx {
   int debug_skip_epilogue = 0;
   unsigned long long* debug_stats = nullptr;   // [128][8] per-layer wait-cycle counters (NHANS_DEBUG_STATS=1)
   int desc_mode = 0;
+  // NHANS_DEBUG_TIMELINE=1: timing events on the three streams for every batch (nhans_debug_timeline)
+  bool timeline = false;
+  cudaEvent_t tl_origin = nullptr;
+  std::vector<std::array<cudaEvent_t, 6>> tl;     // per batch: h2d begin / end, compute begin / end, d2h begin / end
   bool use_walk = true;             // row-walk kernel for the 64-channel stage (NHANS_NO_WALK=1: plain N = 64 GEMM)
   bool use_gen = true;              // resblock1_1_conv2 builds its A operand from the per-frame table (NHANS_NO_GEN=1: window_expand)
   double layer_acc[128][4] = {};
@@ -536,6 +541,22 @@ int ensure_silent(nhans_ctx* ctx) {
   return 0;
 }
 
+// timeline: record timing event `which` of the newest batch on `stream`
+void tl_mark(nhans_ctx* ctx, int which, cudaStream_t stream) {
+  if (!ctx->timeline) return;
+  if (!ctx->tl_origin) {
+    cudaEventCreate(&ctx->tl_origin);
+    cudaEventRecord(ctx->tl_origin, stream);
+  }
+  if (which == 0) {
+    std::array<cudaEvent_t, 6> ev{};
+    for (auto& e : ev) cudaEventCreate(&e);
+    ctx->tl.push_back(ev);
+  }
+  if (ctx->tl.empty()) return;
+  cudaEventRecord(ctx->tl.back()[which], stream);
+}
+
 int check_kernel_flag(nhans_ctx* ctx) {
   if (ctx->err_flag_host && *ctx->err_flag_host) {
     // reported once: the flag is cleared so that a later call (after nhans_load_weights, or on a context whose
@@ -595,6 +616,7 @@ int nhans_create(int device, int variant, int win_capacity, int row_capacity, nh
   if (row_capacity > 0) ctx->row_cap = row_capacity;
   if (const char* dbg = getenv("NHANS_DEBUG_SKIP_EPILOGUE")) ctx->debug_skip_epilogue = atoi(dbg);
   if (const char* dbg = getenv("NHANS_DESC_MODE")) ctx->desc_mode = atoi(dbg);
+  if (const char* dbg = getenv("NHANS_DEBUG_TIMELINE")) ctx->timeline = atoi(dbg) != 0;
   if (const char* dbg = getenv("NHANS_NO_WALK")) ctx->use_walk = atoi(dbg) == 0;
   if (const char* dbg = getenv("NHANS_NO_GEN")) ctx->use_gen = atoi(dbg) == 0;
   if (const char* dbg = getenv("NHANS_DEBUG_STATS")) {
@@ -646,6 +668,8 @@ void nhans_destroy(nhans_ctx* ctx) {
   for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
   for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& ev : ctx->ev_pool) cudaEventDestroy(ev);
+  for (auto& ev : ctx->tl) for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (ctx->tl_origin) cudaEventDestroy(ctx->tl_origin);
   if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -939,6 +963,7 @@ int nhans_upload(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, in
   IoSlot& io = b.io[b.cur];
   cudaStream_t hs = ctx->h2d_stream;
   CK(cudaStreamWaitEvent(hs, io.consumed, 0));
+  tl_mark(ctx, 0, hs);
   CK(io.mix.ensure(b.mix_offs[U] * 2 + 32));
   CK(cudaMemcpyAsync(io.mix.p, mix + mix_offs[0], b.mix_offs[U] * 2, cudaMemcpyHostToDevice, hs));
   CK(io.b.ensure(b.b_offs[U] * 2 + 32));
@@ -953,6 +978,7 @@ int nhans_upload(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_offs, in
   if ((rc = to_device_offs(ctx, io.d_frame_offs, b.frame_offs, hs))) return rc;
   if ((rc = to_device_offs(ctx, io.d_out_offs, b.out_offs, hs))) return rc;
   if ((rc = to_device_offs(ctx, io.d_ctx_frame_offs, b.ctx_frame_offs, hs))) return rc;
+  tl_mark(ctx, 1, hs);
   CK(cudaEventRecord(io.uploaded, hs));
   b.staged = true;
   return NHANS_OK;
@@ -986,6 +1012,7 @@ int nhans_run(nhans_ctx* ctx) {
   // the inputs of this set have landed, and the outputs the set held two batches ago have reached the host
   CK(cudaStreamWaitEvent(ctx->stream, io.uploaded, 0));
   if (io.d2h_pending) CK(cudaStreamWaitEvent(ctx->stream, io.drained, 0));
+  tl_mark(ctx, 2, ctx->stream);
   // front end: a2-a4 for the mixture and the first 200 frames of each context (SN/apply.py:359-387)
   CK(launch_peaks(ctx->stream, io.mix.as<int16_t>(), io.d_mix_offs.as<long long>(), U, b.peak_mix.as<int>()));
   CK(launch_peaks(ctx->stream, io.b.as<int16_t>(), io.d_b_offs.as<long long>(), U, b.peak_b.as<int>()));
@@ -1034,6 +1061,7 @@ int nhans_run(nhans_ctx* ctx) {
                     io.d_out_offs.as<long long>(), U, b.peak_mix.as<int>(), 0, b.max_frames, io.out_f32.as<float>(),
                     io.out_i16.as<int16_t>(), true));
   }
+  tl_mark(ctx, 3, ctx->stream);
   CK(cudaEventRecord(io.consumed, ctx->stream));
   b.done = true;
   return NHANS_OK;
@@ -1054,8 +1082,10 @@ int nhans_download(nhans_ctx* ctx, int16_t* out_i16, float* out_f32, float* mixp
   }
   // the outputs leave on their own stream, so that the next batch can start computing meanwhile
   CK(cudaStreamWaitEvent(ctx->d2h_stream, io.consumed, 0));
+  tl_mark(ctx, 4, ctx->d2h_stream);
   if (out_i16) CK(cudaMemcpyAsync(out_i16, io.out_i16.p, b.total_out * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream));
   if (out_f32) CK(cudaMemcpyAsync(out_f32, io.out_f32.p, b.total_out * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  tl_mark(ctx, 5, ctx->d2h_stream);
   CK(cudaEventRecord(io.drained, ctx->d2h_stream));
   io.d2h_pending = true;
   return NHANS_OK;
@@ -1228,6 +1258,25 @@ int nhans_debug_read_batch(nhans_ctx* ctx, int which, float* out, int64_t n_floa
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, src.p, (size_t)n_floats * 4, cudaMemcpyDeviceToHost));
   return NHANS_OK;
+}
+
+int nhans_debug_timeline(nhans_ctx* ctx, double* out_ms, int max_batches) {
+  if (!ctx || !out_ms || max_batches < 0) return NHANS_ERR_ARG;
+  if (!ctx->timeline || !ctx->tl_origin) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->h2d_stream);
+  cudaStreamSynchronize(ctx->d2h_stream);
+  const int n = std::min<int>(max_batches, (int)ctx->tl.size());
+  const int first = (int)ctx->tl.size() - n;
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 6; ++k) {
+      float ms = -1.f;
+      if (cudaEventElapsedTime(&ms, ctx->tl_origin, ctx->tl[first + i][k]) != cudaSuccess) ms = -1.f;   // never recorded
+      out_ms[6 * i + k] = ms;
+    }
+  cudaGetLastError();
+  return n;
 }
 
 int nhans_device_info(nhans_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* mem_bytes) {

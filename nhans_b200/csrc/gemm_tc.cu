@@ -12,19 +12,26 @@
 //
 //   warp 8   A producer     one TMA box of 136 rows x 64 channels ("slab") per (group, sub-tile): the kw taps
 //                           of a kernel row read the SAME slab through UMMA descriptors whose start address
-//                           is shifted by `shift` rows, so A comes from L2 once per kernel row, not per tap
+//                           is shifted by `shift` rows, so A comes from L2 once per kernel row, not per tap;
+//                           the slabs of a group complete on ONE mbarrier (ring of 4, or 6 for BN <= 128)
 //   warp 9   B producer     one TMA box (BN / 2) x 64 per k-block: each CTA of a pair loads half of B; the
-//                           transactions of both CTAs are credited to the leader's mbarrier
-//   warp 10  MMA issuer     leader CTA only: tcgen05.mma.cta_group::2.kind::f16, M = 256, N = BN, 4 x (K = 16)
-//                           per tap, two sub-tiles interleaved; tcgen05.commit...multicast releases ring
-//                           slots / publishes accumulators in both CTAs
+//                           transactions of both CTAs are credited to the leader's mbarrier, all tiles of a
+//                           group to the barrier of the group's first slot
+//   warp 10  MMA issuer     leader CTA only, ONE elected lane for the whole role (waits, MMAs, commits: two
+//                           barrier waits per group): tcgen05.mma.cta_group::2.kind::f16, M = 256, N = BN,
+//                           4 x (K = 16) per tap, two sub-tiles interleaved; tcgen05.commit...multicast
+//                           releases ring slots / publishes accumulators in both CTAs; split-K for the head
 //   warps 0-7 epilogue      two flavours (kEpiRow): row-per-thread for BN <= 128 (thread = TMEM lane = GEMM
 //                           row, 16 channels per step, 256-bit residual loads and stores, fp16 tables and
 //                           per-channel vectors in shared memory, no staging) and transposing for BN = 256
 //                           (tcgen05.ld -> XOR-swizzled fp32 transpose -> 4 lanes per row, coalesced).
 //                           + per-utterance conditioning bias + time / frequency embedding tables + scaled
 //                           identity residual / rank-1 transform -> ReLU -> fp16 into the consumer's grid
-//                           (or fp32 + centre frame for the head)
+//                           (or, for the head, raw fp32 partial sums of one K split: head_reduce_kernel
+//                           adds the splits, the column scale, the bias and the centre frame)
+//
+// The 64-channel stride-1 layers of the mask network run on conv_walk.cu instead (this kernel remains their
+// NHANS_NO_WALK fallback as a plain N = 64 GEMM, and round 1's pixel-pair form behind NHANS_STAGE1=pair).
 //
 // The epilogue is the fusion of blocks.py:104-108 (batch-norm), main.py:166,172 (conditioning adds),
 // main.py:184-186 (residual add, ReLU) folded as in SURVEY.md App. A.6.
