@@ -45,7 +45,7 @@ constexpr int kThreads = kIW * 32;      // inverse kernels
 __device__ float2 g_tw200[200];         // e^{-2 pi i t / 200}
 __device__ float2 g_tw400[201];         // e^{-2 pi i k / 400}
 __device__ __align__(16) float g_hann[400];           // 0.5 - 0.5 cos(2 pi n / 400)
-__device__ __align__(16) float g_winv[400];           // hann[n] / sum_j hann^2[n mod 160 + 160 j]
+__device__ __align__(16) float g_winv[400];           // hann[n] / sum_j hann^2[n mod 160 + 160 j] / 400
 
 using namespace fft;
 
@@ -172,7 +172,7 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
       const int m = 25 * m1 + m2;
       const float2 xx = *reinterpret_cast<const float2*>(&x0[f * kHop + 2 * m]);
       const float2 h = __ldg(reinterpret_cast<const float2*>(g_hann) + m);
-      v[m1] = make_float2(xx.x * h.x, xx.y * h.y);
+      v[m1] = cmul2(xx, h);
     }
     dft8<false>(v);
     z[f * 200 + m2] = v[0];
@@ -199,12 +199,14 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
     const float2 a = z[f * 200 + k];
     const float2 b = z[f * 200 + (k ? 200 - k : 0)];
     const float2 w = __ldg(&g_tw400[k]);
-    const float ex = 0.5f * (a.x + b.x), ey = 0.5f * (a.y - b.y);
-    const float ox = 0.5f * (a.x - b.x), oy = 0.5f * (a.y + b.y);
-    const float px = w.x * ox - w.y * oy, py = w.x * oy + w.y * ox;
+    const float2 cb = cconj(b);
+    const float2 E = cscale(cadd(a, cb), 0.5f), O = cscale(csub(a, cb), 0.5f);
+    const float2 P = cmul(w, O);
+    const float2 Xk = cadd(E, rot<false>(P));                        // E - i P
+    const float2 Xm = csub(cconj(E), make_float2(P.y, P.x));         // conj(E) - i conj(P)
     const int o = f * kBinsD;
-    emit_bin<PHASOR>(ex + py, ey - px, o + k, lm_w, ph_w);
-    if (k != 100) emit_bin<PHASOR>(ex - py, -ey - px, o + 200 - k, lm_w, ph_w);
+    emit_bin<PHASOR>(Xk.x, Xk.y, o + k, lm_w, ph_w);
+    if (k != 100) emit_bin<PHASOR>(Xm.x, Xm.y, o + 200 - k, lm_w, ph_w);
     k += 32;
     if (k >= 101) { k -= 101; f += 1; }
   }
@@ -242,8 +244,8 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
       const float ak = __expf(logmag[o + k]), am = __expf(logmag[o + 200 - k]);
       if (PHASOR) {
         const float2 pk = reinterpret_cast<const float2*>(phase)[o + k], pm = reinterpret_cast<const float2*>(phase)[o + 200 - k];
-        sk = make_float2(ak * pk.x, ak * pk.y);
-        sm = make_float2(am * pm.x, am * pm.y);
+        sk = cscale(pk, ak);
+        sm = cscale(pm, am);
       } else {
         float sn, cs;
         sincosf(phase[o + k], &sn, &cs);
@@ -254,10 +256,11 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
       if (k == 0) { sk.y = 0.f; sm.y = 0.f; }           // irfft ignores the imaginary part of DC / Nyquist
     }
     const float2 w = __ldg(&g_tw400[k]);                 // conj(w) = e^{+2 pi i k / 400}
-    const float ex = sk.x + sm.x, ey = sk.y - sm.y, dx = sk.x - sm.x, dy = sk.y + sm.y;
-    const float wx = w.x * dx + w.y * dy, wy = w.x * dy - w.y * dx;          // conj(w) * d
-    z[f * 200 + k] = make_float2(ex - wy, ey + wx);
-    if (k > 0 && k < 100) z[f * 200 + 200 - k] = make_float2(ex + wy, wx - ey);
+    const float2 cm = cconj(sm);
+    const float2 e = cadd(sk, cm), d = csub(sk, cm);
+    const float2 wd = cmul(cconj(w), d);
+    z[f * 200 + k] = cadd(e, rot<true>(wd));                                  // e + i wd
+    if (k > 0 && k < 100) z[f * 200 + 200 - k] = cadd(cconj(e), make_float2(wd.y, wd.x));
     k += 32;
     if (k >= 101) { k -= 101; f += 1; }
   }
@@ -285,7 +288,7 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
   for (int i = lane, m = lane; i < kFW * 200; i += 32) {
     const float2 v = z[i];
     const float2 w = __ldg(reinterpret_cast<const float2*>(g_winv) + m);
-    z[i] = make_float2(v.x * (1.0f / 400.0f) * w.x, v.y * (1.0f / 400.0f) * w.y);
+    z[i] = cmul2(v, w);                                  // g_winv carries the 1 / 400 of the inverse transform
     m += 32;
     if (m >= 200) m -= 200;
   }
@@ -446,7 +449,7 @@ cudaError_t dsp_init_tables() {
       int n = (i % 160) + 160 * j;
       if (n < 400) d += (double)hann[n] * (double)hann[n];
     }
-    winv[i] = (float)((double)hann[i] / d);
+    winv[i] = (float)((double)hann[i] / d / 400.0);       // synthesis window x the 1 / N of the unnormalised inverse DFT
   }
   cudaError_t e;
   if ((e = cudaMemcpyToSymbol(g_tw200, t200.data(), sizeof(float2) * 200)) != cudaSuccess) return e;

@@ -10,9 +10,46 @@
 namespace nhans {
 namespace fft {
 
-NHANS_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-NHANS_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-NHANS_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex helpers.  On the device they are Blackwell's packed fp32x2 instructions (add / sub / mul / fma.rn.f32x2 ->
+// FADD2 / FMUL2 / FFMA2 in SASS: one issue slot for both components; ptxas folds component swaps, negations and
+// scalar broadcasts into the operand selectors, so multiplying by +-i or by a real constant costs nothing extra).
+// The STFT kernels are issue bound, and half of their instructions were scalar fp32 adds / multiplies on (re, im)
+// pairs.  The host versions (tests/host/fft_check.cu) are the plain scalar formulas.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long f2_bits(float2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) {          // component-wise product
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 cfma2(float2 a, float2 b, float2 c) { // component-wise a * b + c
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(r);
+}
+#else
+inline float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+inline float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 cfma2(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#endif
+NHANS_HD float2 cscale(float2 a, float s) { return cmul2(a, make_float2(s, s)); }                 // a * s
+NHANS_HD float2 caxpy(float2 a, float s, float2 c) { return cfma2(a, make_float2(s, s), c); }     // a * s + c
+// complex product a * b = a.x * b + a.y * (i b)
+NHANS_HD float2 cmul(float2 a, float2 b) {
+  return cfma2(make_float2(a.x, a.x), b, cmul2(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+}
 NHANS_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by -i (forward) or +i (inverse)
 template <bool INV>
@@ -33,9 +70,10 @@ NHANS_HD void dft8(float2 (&v)[8]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) { a[j] = cadd(v[j], v[j + 4]); b[j] = csub(v[j], v[j + 4]); }
   // b[j] *= W8^j  (forward W8 = e^{-i pi/4})
-  b[1] = INV ? make_float2((b[1].x - b[1].y) * r, (b[1].x + b[1].y) * r) : make_float2((b[1].x + b[1].y) * r, (b[1].y - b[1].x) * r);
+  // W8 b = (b + rot(b)) / sqrt 2,  W8^3 b = (rot(b) - b) / sqrt 2   (rot = multiplication by -+i)
+  b[1] = cscale(cadd(b[1], rot<INV>(b[1])), r);
   b[2] = rot<INV>(b[2]);
-  b[3] = INV ? make_float2((-b[3].x - b[3].y) * r, (b[3].x - b[3].y) * r) : make_float2((b[3].y - b[3].x) * r, (-b[3].x - b[3].y) * r);
+  b[3] = cscale(csub(rot<INV>(b[3]), b[3]), r);
   dft4<INV>(a[0], a[1], a[2], a[3], v[0], v[2], v[4], v[6]);
   dft4<INV>(b[0], b[1], b[2], b[3], v[1], v[3], v[5], v[7]);
 }
@@ -45,11 +83,11 @@ NHANS_HD void dft5(float2 x0, float2 x1, float2 x2, float2 x3, float2 x4, float2
   const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
   const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
   float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
-  y0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
-  float2 m1 = make_float2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
-  float2 m2 = make_float2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
-  float2 u1 = rot<INV>(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-  float2 u2 = rot<INV>(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+  y0 = cadd(cadd(x0, t1), t2);
+  float2 m1 = caxpy(t2, c2, caxpy(t1, c1, x0));
+  float2 m2 = caxpy(t2, c1, caxpy(t1, c2, x0));
+  float2 u1 = rot<INV>(caxpy(t4, s2, cscale(t3, s1)));
+  float2 u2 = rot<INV>(caxpy(t4, -s1, cscale(t3, s2)));
   y1 = cadd(m1, u1); y4 = csub(m1, u1); y2 = cadd(m2, u2); y3 = csub(m2, u2);
 }
 

@@ -2,10 +2,12 @@
 # what the driver runs at round end, on one B200: GPU tests, smoke, both bench arms with its step counts
 set -u
 mkdir -p gpurun_out
+if [ "${SKIP_TESTS:-0}" = 0 ]; then
 timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/r2d_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/r2d_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?"
-/usr/bin/time -v timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 3 > gpurun_out/r2d_ref.json 2> gpurun_out/r2d_ref.err; echo "ref rc=$?"; grep -E "Elapsed" gpurun_out/r2d_ref.err; cut -c1-200 gpurun_out/r2d_ref.json
-/usr/bin/time -v timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/r2d_bench.json 2> gpurun_out/r2d_bench.err; echo "bench rc=$?"; grep -E "Elapsed" gpurun_out/r2d_bench.err
+fi
+S=$SECONDS; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 3 > gpurun_out/r2d_ref.json 2> gpurun_out/r2d_ref.err; echo "ref rc=$? wall $((SECONDS-S)) s"
+S=$SECONDS; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/r2d_bench.json 2> gpurun_out/r2d_bench.err; echo "bench rc=$? wall $((SECONDS-S)) s"
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r2d_bench.json").read().strip().splitlines()[-1])
