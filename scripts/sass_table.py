@@ -1,7 +1,7 @@
 """Per-kernel SASS mnemonic table of the built library (no GPU needed): proves which kernels use the Blackwell paths.
    python scripts/sass_table.py > profiles/r02_sass_table.txt
 UTCHMMA = tcgen05.mma, .2CTA = cta_group::2, UTMALDG = TMA tensor load, UBLKCP = 1-D bulk copy, LDTM = tcgen05.ld,
-UTCBAR = tcgen05.commit, SYNCS = mbarrier, UTCATOMSWS / UTCCP etc. would show TMEM management."""
+UTCBAR = tcgen05.commit, SYNCS = mbarrier, FFMA2 / FADD2 / FMUL2 = packed fp32x2 arithmetic."""
 import collections
 import os
 import re
@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "nhans_b200", "libnhans_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "ELECT", "HMMA", "FFMA", "DFMA", "MUFU", "SHFL", "LDG", "STG", "LDS", "STS"]
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "ELECT", "HMMA", "FFMA", "FFMA2", "FADD2", "FMUL2", "DFMA", "MUFU", "SHFL", "LDG", "STG", "LDS", "STS"]
 tab = collections.OrderedDict()
 cur = None
 for line in out.splitlines():
