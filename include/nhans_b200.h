@@ -84,6 +84,17 @@ int nhans_istft(nhans_ctx* ctx, const float* logmag, const float* phase, const i
 
 /* ---- fused end-to-end path: what apply_snc / apply_separator and the benchmark call ------------------ */
 
+/* The same path for FLOAT clips that are already normalised / mixed on the host, fused on the device: apply_demo
+ * (SN/apply.py:212-337, SS/apply.py:179-285: the on-the-fly mixture and the scaled context signals of combine_signals) and
+ * stereo files of apply_snc / apply_separator (float64 channel mean, SN/apply.py:46-53).  Contexts are the first 200 STFT
+ * frames of ctx_a / ctx_b (ctx_a may be NULL for the selective-noise variant: Silent.wav); the mask network runs over
+ * mixture frames [start_frame, T_u) of every utterance (0 = apply_snc, 200 = apply_demo, SN/apply.py:251-262), the slice
+ * zero padded like a whole utterance.  out_offs [U+1] is written ((T_u - start_frame - 1) * 160 + 400 samples each); call with
+ * out_f32 = mixproc_f32 = NULL first to size the outputs ('mixed_demo.wav' / 'mixed_processed.wav' = mixproc).  Synchronous. */
+int nhans_enhance_f32(nhans_ctx* ctx, const float* mix, const int64_t* mix_offs, int U, const float* ctx_a, const int64_t* a_offs,
+                      const float* ctx_b, const int64_t* b_offs, int start_frame, float* out_f32, float* mixproc_f32,
+                      int64_t* out_offs);
+
 /* Output sizes for a batch: out_offs [U+1] in samples (trimmed lengths), without touching the GPU. */
 int nhans_output_offsets(const int64_t* mix_offs, int U, int64_t* out_offs);
 

@@ -13,7 +13,7 @@ SO_PATH = os.environ.get("NHANS_B200_LIB") or os.path.join(_HERE, "libnhans_b200
 SYMBOLS = [
     "nhans_create", "nhans_destroy", "nhans_last_error", "nhans_load_weights", "nhans_normalise", "nhans_stft",
     "nhans_stft_f32", "nhans_eval_loss",
-    "nhans_embed", "nhans_masknet", "nhans_istft", "nhans_output_offsets", "nhans_enhance_batch", "nhans_sync", "nhans_sync_previous",
+    "nhans_embed", "nhans_masknet", "nhans_istft", "nhans_output_offsets", "nhans_enhance_batch", "nhans_enhance_f32", "nhans_sync", "nhans_sync_previous",
     "nhans_upload", "nhans_run", "nhans_download", "nhans_postmix", "nhans_host_alloc", "nhans_host_free", "nhans_event_record",
     "nhans_event_elapsed_ms", "nhans_profile_enable", "nhans_profile_get", "nhans_profile_reset",
     "nhans_profile_get_layer", "nhans_plan_json",
@@ -64,6 +64,7 @@ def load():
     lib.nhans_download.argtypes = [vp, vp, vp, vp]
     lib.nhans_postmix.argtypes = [vp, c.c_float, i32, vp, vp, vp, vp]
     lib.nhans_sync.argtypes = [vp]
+    lib.nhans_enhance_f32.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.nhans_sync_previous.argtypes = [vp]
     lib.nhans_host_alloc.argtypes = [i64, c.POINTER(vp)]
     lib.nhans_host_free.argtypes = [vp]

@@ -123,6 +123,7 @@ struct nhans_ctx {
   bool silent_ready = false;
   Batch batch;
   DBuf tmp[8];
+  DBuf fbuf[12];                    // nhans_enhance_f32 staging (float clips, offsets, compacted spectra)
   cudaEvent_t events[16] = {};
   bool profile = false;
   std::vector<ProfRec> prof;
@@ -665,6 +666,7 @@ void nhans_destroy(nhans_ctx* ctx) {
                   &b.snr, &ctx->silent_emb})
     d->release();
   for (auto& t : ctx->tmp) t.release();
+  for (auto& t : ctx->fbuf) t.release();
   for (auto& ev : ctx->events) if (ev) cudaEventDestroy(ev);
   for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& ev : ctx->ev_pool) cudaEventDestroy(ev);
@@ -1127,6 +1129,129 @@ int nhans_enhance_batch(nhans_ctx* ctx, const int16_t* mix, const int64_t* mix_o
   if ((rc = nhans_upload(ctx, mix, mix_offs, U, ctx_a, a_offs, ctx_b, b_offs))) return rc;
   if ((rc = nhans_run(ctx))) return rc;
   return nhans_download(ctx, out_i16, out_f32, mixproc_f32);
+}
+
+int nhans_enhance_f32(nhans_ctx* ctx, const float* mix, const int64_t* mix_offs, int U, const float* ctx_a, const int64_t* a_offs,
+                      const float* ctx_b, const int64_t* b_offs, int start_frame, float* out_f32, float* mixproc_f32, int64_t* out_offs) {
+  if (!ctx || !mix || !mix_offs || !ctx_b || !b_offs || !out_offs || U <= 0 || start_frame < 0) return fail(ctx, NHANS_ERR_ARG, "bad arguments");
+  if (ctx_a && !a_offs) return fail(ctx, NHANS_ERR_ARG, "ctx_a given without offsets");
+  if (!ctx_a && ctx->variant != NHANS_VARIANT_SELECTIVE_NOISE) return fail(ctx, NHANS_ERR_ARG, "the separator needs both context recordings");
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = need_weights(ctx))) return rc;
+  std::vector<long long> mo(U + 1), ao(U + 1, 0), bo(U + 1), fo(U + 1, 0), fc(U + 1, 0), oo(U + 1, 0), cfo(U + 1);
+  int max_frames = 0, max_c = 0;
+  for (int u = 0; u <= U; ++u) {
+    mo[u] = mix_offs[u] - mix_offs[0];
+    bo[u] = b_offs[u] - b_offs[0];
+    if (ctx_a) ao[u] = a_offs[u] - a_offs[0];
+    cfo[u] = (long long)u * kCtxFrames;
+  }
+  for (int u = 0; u < U; ++u) {
+    const int T = frames_of(mo[u + 1] - mo[u]);
+    if (T <= start_frame) return fail(ctx, NHANS_ERR_ARG, "utterance " + std::to_string(u) + " has " + std::to_string(T) + " <= start_frame frames");
+    if (frames_of(bo[u + 1] - bo[u]) < kCtxFrames || (ctx_a && frames_of(ao[u + 1] - ao[u]) < kCtxFrames))
+      return fail(ctx, NHANS_ERR_CONTEXT_TOO_SHORT,
+                  "context signal of utterance " + std::to_string(u) + " yields fewer than 200 STFT frames (needs >= 32240 samples)");
+    max_frames = std::max(max_frames, T);
+    max_c = std::max(max_c, T - start_frame);
+    fo[u + 1] = fo[u] + T;
+    fc[u + 1] = fc[u] + (T - start_frame);
+    oo[u + 1] = oo[u] + (long long)(T - start_frame - 1) * 160 + 400;
+  }
+  for (int u = 0; u <= U; ++u) out_offs[u] = oo[u];
+  if (!out_f32 && !mixproc_f32) return NHANS_OK;
+  // the shared spectra / embedding buffers are about to be reused: nothing of an earlier batch may still be running
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->h2d_stream));
+  CK(cudaStreamSynchronize(ctx->d2h_stream));
+  Batch& b = ctx->batch;
+  b.done = false; b.staged = false;
+  DBuf* F = ctx->fbuf;
+  cudaStream_t st = ctx->stream;
+  const size_t sbytes = (size_t)fo[U] * kBins * 4, cbytes = (size_t)fc[U] * kBins * 4, xbytes = (size_t)U * kCtxFrames * kBins * 4;
+  const int n_cols = ctx->main_net.plan.cond.n_cols;
+  CK(F[0].ensure(mo[U] * 4 + 16));
+  CK(cudaMemcpyAsync(F[0].p, mix + mix_offs[0], mo[U] * 4, cudaMemcpyHostToDevice, st));
+  CK(F[1].ensure(bo[U] * 4 + 16));
+  CK(cudaMemcpyAsync(F[1].p, ctx_b + b_offs[0], bo[U] * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = to_device_offs(ctx, F[3], mo))) return rc;
+  if ((rc = to_device_offs(ctx, F[4], bo))) return rc;
+  if ((rc = to_device_offs(ctx, F[6], fo))) return rc;
+  if ((rc = to_device_offs(ctx, F[7], fc))) return rc;
+  if ((rc = to_device_offs(ctx, F[8], oo))) return rc;
+  if ((rc = to_device_offs(ctx, F[9], cfo))) return rc;
+  CK(b.logmag.ensure(sbytes + 4));
+  CK(b.phase.ensure(2 * sbytes + 8));
+  CK(b.den.ensure(cbytes + 4));
+  CK(b.ctxlm_b.ensure(xbytes));
+  CK(b.emb_b.ensure((size_t)U * 512 * 4));
+  CK(b.cond.ensure((size_t)U * n_cols * 4));
+  CK(b.peak_mix.ensure(sizeof(int) * U));
+  CK(cudaMemsetAsync(b.peak_mix.p, 0, sizeof(int) * U, st));           // no int16 output on this path
+  {
+    ProfScope ps(ctx, 1, 0, 4.0 * mo[U] + 3.0 * sbytes);
+    CK(launch_stft_f32(st, F[0].as<float>(), F[3].as<long long>(), F[6].as<long long>(), U, max_frames, b.logmag.as<float>(),
+                       b.phase.as<float>(), true));
+  }
+  CK(launch_stft_f32(st, F[1].as<float>(), F[4].as<long long>(), F[9].as<long long>(), U, kCtxFrames, b.ctxlm_b.as<float>(), nullptr));
+  ctx->launches += 1;
+  const float* emb_a = nullptr;
+  int stride_a = 0;
+  if (ctx_a) {
+    CK(F[2].ensure(ao[U] * 4 + 16));
+    CK(cudaMemcpyAsync(F[2].p, ctx_a + a_offs[0], ao[U] * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = to_device_offs(ctx, F[5], ao))) return rc;
+    CK(b.ctxlm_a.ensure(xbytes));
+    CK(b.emb_a.ensure((size_t)U * 512 * 4));
+    CK(launch_stft_f32(st, F[2].as<float>(), F[5].as<long long>(), F[9].as<long long>(), U, kCtxFrames, b.ctxlm_a.as<float>(), nullptr));
+    ctx->launches += 1;
+    if ((rc = run_tower(ctx, b.ctxlm_a.as<float>(), U, b.emb_a.as<float>()))) return rc;
+    emb_a = b.emb_a.as<float>();
+    stride_a = 512;
+  } else {
+    if ((rc = ensure_silent(ctx))) return rc;
+    emb_a = ctx->silent_emb.as<float>();
+  }
+  if ((rc = run_tower(ctx, b.ctxlm_b.as<float>(), U, b.emb_b.as<float>()))) return rc;
+  CK(launch_cond_table(st, emb_a, stride_a, b.emb_b.as<float>(), 512, U, ctx->main_net.Pa, ctx->main_net.Pb, ctx->main_net.c, n_cols,
+                       b.cond.as<float>()));
+  ctx->launches += 1;
+  // frames [start_frame, T_u) of every utterance, compacted: the slice is processed like a whole utterance
+  const float* lm_c = b.logmag.as<float>();
+  const float* ph_c = b.phase.as<float>();
+  if (start_frame > 0) {
+    CK(F[10].ensure(cbytes + 4));
+    CK(F[11].ensure(2 * cbytes + 8));
+    for (int u = 0; u < U; ++u) {
+      const size_t rows = (size_t)(fc[u + 1] - fc[u]) * kBins;
+      const size_t src = (size_t)(fo[u] + start_frame) * kBins, dst = (size_t)fc[u] * kBins;
+      CK(cudaMemcpyAsync(F[10].as<float>() + dst, b.logmag.as<float>() + src, rows * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(F[11].as<float>() + 2 * dst, b.phase.as<float>() + 2 * src, rows * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    lm_c = F[10].as<float>();
+    ph_c = F[11].as<float>();
+  }
+  if ((rc = run_masknet(ctx, lm_c, F[7].as<long long>(), fc.data(), U, fc[U], b.cond.as<float>(), b.den.as<float>()))) return rc;
+  IoSlot& io = b.io[b.cur];
+  CK(io.out_f32.ensure(oo[U] * 4 + 16));
+  if (out_f32) {
+    ProfScope ps(ctx, 2, 0, 3.0 * cbytes + 4.0 * oo[U]);
+    CK(launch_istft(st, b.den.as<float>(), ph_c, F[7].as<long long>(), F[8].as<long long>(), U, b.peak_mix.as<int>(), 0, max_c,
+                    io.out_f32.as<float>(), nullptr, true));
+    CK(cudaMemcpyAsync(out_f32, io.out_f32.p, oo[U] * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (mixproc_f32) {
+    CK(b.mixproc.ensure(oo[U] * 4 + 16));
+    ProfScope ps(ctx, 2, 0, 3.0 * cbytes + 4.0 * oo[U]);
+    CK(launch_istft(st, lm_c, ph_c, F[7].as<long long>(), F[8].as<long long>(), U, b.peak_mix.as<int>(), 0, max_c, b.mixproc.as<float>(),
+                    nullptr, true));
+    CK(cudaMemcpyAsync(mixproc_f32, b.mixproc.p, oo[U] * 4, cudaMemcpyDeviceToHost, st));
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if ((rc = check_kernel_flag(ctx))) return rc;
+  CK(e);
+  return NHANS_OK;
 }
 
 int nhans_sync(nhans_ctx* ctx) {

@@ -477,10 +477,11 @@ cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* off
 }
 
 cudaError_t launch_stft_f32(cudaStream_t s, const float* x, const long long* offs, const long long* frame_offs, int U,
-                            int max_frames_per_clip, float* logmag, float* phase) {
+                            int max_frames_per_clip, float* logmag, float* phase, bool phasor) {
   if (U <= 0 || max_frames_per_clip <= 0) return cudaSuccess;
   dim3 grid((max_frames_per_clip + kFB - 1) / kFB, U);
-  stft_kernel<false><<<grid, kSW * 32, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
+  if (phasor) stft_kernel<true><<<grid, kSW * 32, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
+  else stft_kernel<false><<<grid, kSW * 32, 0, s>>>(nullptr, x, offs, frame_offs, nullptr, logmag, phase);
   return cudaGetLastError();
 }
 

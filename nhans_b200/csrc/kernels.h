@@ -173,7 +173,7 @@ cudaError_t launch_stft(cudaStream_t s, const int16_t* pcm, const long long* off
                         bool phasor = false);   // phasor: `phase` receives unit phasors (float2 per bin) instead of angles
 cudaError_t launch_eval_loss(cudaStream_t s, const float* den, const float* tgt, long long n, float* loss);
 cudaError_t launch_stft_f32(cudaStream_t s, const float* x, const long long* offs, const long long* frame_offs, int U,
-                            int max_frames_per_clip, float* logmag, float* phase);
+                            int max_frames_per_clip, float* logmag, float* phase, bool phasor = false);
 // exp(logmag) * e^{j phase} -> irfft-400 -> synthesis window -> overlap-add -> f32 / int16 samples
 cudaError_t launch_istft(cudaStream_t s, const float* logmag, const float* phase, const long long* frame_offs,
                          const long long* out_offs, int U, const int* peak, long long total_blocks_hint,

@@ -142,56 +142,49 @@ class Engine:
         self._ck(self.lib.nhans_stft_f32(self.h, _ptr(data), _ptr(offs), U, _ptr(lm), _ptr(ph), _ptr(fo)))
         return lm, ph, fo
 
+    def enhance_f32(self, mixes, ctx_a, ctx_b, start=0, want_mixproc=True):
+        """Fused float path (nhans_enhance_f32): lists of float sample arrays that are already normalised / mixed on the
+        host; contexts = first 200 frames of ctx_a[u] / ctx_b[u] (ctx_a may be None: Silent.wav); the mask network runs
+        over mixture frames [start:].  One device pass, no host round trips between the stages.
+        -> (list of denoised sample arrays, list of mixture-centre sample arrays or None)"""
+        def packf(clips):
+            offs = np.zeros(len(clips) + 1, np.int64)
+            for i, c in enumerate(clips):
+                offs[i + 1] = offs[i] + len(c)
+            return np.ascontiguousarray(np.concatenate([np.asarray(c, np.float32) for c in clips])), offs
+        m, mo = packf(mixes)
+        b, bo = packf(ctx_b)
+        a, ao = packf(ctx_a) if ctx_a is not None else (None, None)
+        U = len(mixes)
+        oo = np.zeros(U + 1, np.int64)
+        self._ck(self.lib.nhans_enhance_f32(self.h, _ptr(m), _ptr(mo), U, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), int(start), None, None, _ptr(oo)))
+        y = np.zeros(int(oo[-1]), np.float32)
+        ym = np.zeros(int(oo[-1]), np.float32) if want_mixproc else None
+        self._ck(self.lib.nhans_enhance_f32(self.h, _ptr(m), _ptr(mo), U, _ptr(a), _ptr(ao), _ptr(b), _ptr(bo), int(start), _ptr(y), _ptr(ym), _ptr(oo)))
+        return unpack(y, oo), (unpack(ym, oo) if want_mixproc else None)
+
     def enhance_demo(self, mix, sig_a, sig_b, start=CTX_FRAMES):
         """apply_demo (SN/apply.py:247-337, SS/apply.py:198-285): float mixture + two float context signals.
         Contexts are the first 200 frames of sig_a / sig_b, windows are taken over mix frames [start:] only (the
         slice is zero padded like a whole utterance).  -> (denoised samples, mixture-centre samples)."""
-        lm, ph, fo = self.stft_f32([mix, sig_a, sig_b])
-        T = int(fo[1])
-        for u in (1, 2):
-            if fo[u + 1] - fo[u] < CTX_FRAMES:
-                raise NhansError(-4, "context signal yields %d < 200 STFT frames" % (fo[u + 1] - fo[u]))
-        if T <= start:
-            raise NhansError(-2, "the mixture has %d <= %d frames" % (T, start))
-        ctx = np.stack([lm[fo[1]:fo[1] + CTX_FRAMES], lm[fo[2]:fo[2] + CTX_FRAMES]])
-        emb = self.embed(ctx)
-        sl = np.ascontiguousarray(lm[start:T])
-        sp = np.ascontiguousarray(ph[start:T])
-        f1 = np.array([0, T - start], np.int64)
-        den = self.masknet(sl, f1, emb[0:1], emb[1:2])
-        y, _ = self.istft(den, sp, f1)
-        ymix, _ = self.istft(sl, sp, f1)
-        return y, ymix
+        y, ymix = self.enhance_f32([mix], [sig_a], [sig_b], start=start)
+        return y[0], ymix[0]
 
     def enhance_float(self, mix, ctx_a, ctx_b):
         """apply_snc / apply_separator for clips that are not int16 PCM (stereo files averaged in float64,
-        SN/apply.py:46-53): host normalisation exactly like handle_signals (SN/apply.py:142-163), then the stage entry
-        points - float STFT, towers on the first 200 context frames, mask network over every frame, inverse STFT.
-        ctx_a may be None (Silent.wav).  -> dict(f32=denoised samples, mixed_processed=..., peak=max|mix|)."""
+        SN/apply.py:46-53): host normalisation exactly like handle_signals (SN/apply.py:142-163), then the fused float
+        entry point.  ctx_a may be None (Silent.wav).  -> dict(f32=denoised samples, mixed_processed=..., peak=max|mix|)."""
         from .wavio import normalise_host
         m = normalise_host(mix)
         if len(m) >= 400:
             m = m[:len(m) - (len(m) - 400) % 160]
-        sigs = [m, normalise_host(ctx_b)] + ([normalise_host(ctx_a)] if ctx_a is not None else [])
-        lm, ph, fo = self.stft_f32(sigs)
-        T = int(fo[1])
-        if T <= 0:
-            z = np.zeros(0, np.float32)
-            return dict(f32=z, mixed_processed=z, peak=0.0)
-        for u in range(1, len(sigs)):
-            if fo[u + 1] - fo[u] < CTX_FRAMES:
-                raise NhansError(-4, "context clip yields %d < 200 STFT frames (needs >= 32240 samples)" % (fo[u + 1] - fo[u]))
-        ctx_b_lm = lm[fo[1]:fo[1] + CTX_FRAMES]
-        ctx_a_lm = (lm[fo[2]:fo[2] + CTX_FRAMES] if ctx_a is not None
-                    else np.full((CTX_FRAMES, N_BINS), np.log(np.float32(1e-5)), np.float32))     # all-zero Silent.wav
-        emb = self.embed(np.stack([ctx_a_lm, ctx_b_lm]))
-        sl, sp = np.ascontiguousarray(lm[:T]), np.ascontiguousarray(ph[:T])
-        f1 = np.array([0, T], np.int64)
-        den = self.masknet(sl, f1, emb[0:1], emb[1:2])
-        y, _ = self.istft(den, sp, f1)
-        ymix, _ = self.istft(sl, sp, f1)
         x = np.asarray(mix)
-        return dict(f32=y, mixed_processed=ymix, peak=float(max(abs(x))) if len(x) else 0.0)
+        peak = float(max(abs(x))) if len(x) else 0.0
+        if len(m) < 400:
+            z = np.zeros(0, np.float32)
+            return dict(f32=z, mixed_processed=z, peak=peak)
+        y, ymix = self.enhance_f32([m], None if ctx_a is None else [normalise_host(ctx_a)], [normalise_host(ctx_b)], start=0)
+        return dict(f32=y[0], mixed_processed=ymix[0], peak=peak)
 
     def eval_loss(self, denoised, target):
         """example_loss of the model graph (SN/main.py:243-246): [n,201] x [n,201] -> [n]."""

@@ -163,3 +163,36 @@ def test_trained_checkpoint_end_to_end_when_mounted():
         eng.close()
     ref = O.apply_arrays(O.Net(w, W.SEPARATOR), mix, itf, tgt)
     assert _snr(ref, got) >= 40.0
+
+
+def test_fused_float_path_matches_stage_entries(engine_sn):
+    """nhans_enhance_f32 (one device pass: float STFT with unit phasors, towers on the first 200 context frames, mask
+    network over frames [start:], inverse STFT) against the same computation assembled from the stage entry points
+    (angles, host round trips) - two utterances, start = 200 (apply_demo) and start = 0 (stereo apply_snc)."""
+    from nhans_b200.wavio import normalise_host
+    mixes = [normalise_host(synth.mixture(3.0, 41)), normalise_host(synth.mixture(2.7, 42))]
+    ca = [normalise_host(synth.noise_clip(41, "pos")), normalise_host(synth.noise_clip(42, "pos"))]
+    cb = [normalise_host(synth.noise_clip(41, "neg")), normalise_host(synth.noise_clip(42, "neg"))]
+    for start in (200, 0):
+        y, ym = engine_sn.enhance_f32(mixes, ca, cb, start=start)
+        for u in range(2):
+            lm, ph, fo = engine_sn.stft_f32([mixes[u], ca[u], cb[u]])
+            T = int(fo[1])
+            emb = engine_sn.embed(np.stack([lm[fo[1]:fo[1] + 200], lm[fo[2]:fo[2] + 200]]))
+            sl, sp = np.ascontiguousarray(lm[start:T]), np.ascontiguousarray(ph[start:T])
+            f1 = np.array([0, T - start], np.int64)
+            den = engine_sn.masknet(sl, f1, emb[0:1], emb[1:2])
+            ys, _ = engine_sn.istft(den, sp, f1)
+            ysm, _ = engine_sn.istft(sl, sp, f1)
+            assert len(y[u]) == len(ys) == (T - start - 1) * 160 + 400
+            assert _snr(ys, y[u]) >= 60.0 and _snr(ysm, ym[u]) >= 80.0
+    # Silent positive context (ctx_a = None) == an explicit all-zero clip
+    y0, _ = engine_sn.enhance_f32(mixes[:1], None, cb[:1], start=0)
+    y1, _ = engine_sn.enhance_f32(mixes[:1], [np.zeros(48000, np.float32)], cb[:1], start=0)
+    assert _snr(y1[0], y0[0]) >= 80.0
+    from nhans_b200.engine import NhansError
+    with pytest.raises(NhansError) as ei:
+        engine_sn.enhance_f32(mixes[:1], None, [cb[0][:16000]], start=0)          # 1 s context: < 200 frames
+    assert ei.value.code == -4
+    with pytest.raises(NhansError):
+        engine_sn.enhance_f32([mixes[0][:16000]], None, cb[:1], start=200)         # 98 frames <= start
