@@ -225,38 +225,38 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     ptx::tc_fence_after();
     uint32_t aslot = 0, aphase = 0;
     long long seq = 0;
+    // barrier waits of one step: the slots it claims must have been read by the epilogue, its slab must have landed
+    auto wait_step = [&](long long sq, int r, uint32_t slot, uint32_t phase) {
+      const WalkWin w = walk_window(sq, r, H, p.pt);
+      for (int c = 0; c < w.n_fresh; ++c) {
+        const long long J = sq * H + w.o_lo + w.n - w.n_fresh + c;
+        ptx::mbar_wait_timed(&ctrl->tmem_empty[J & (kWalkSlots - 1)], (uint32_t)(((J >> 3) & 1) ^ 1), p.err_flag, 2, &w_tmem);
+      }
+      ptx::mbar_wait_timed(&ctrl->a_full[slot], phase, p.err_flag, 3, &w_a);
+    };
+    if ((int)blockIdx.x < num_tiles) wait_step(0, 0, 0, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
       const long long j0 = seq * H;
       for (int r = 0; r < H; ++r) {
         const WalkWin w = walk_window(seq, r, H, p.pt);
-        for (int c = 0; c < w.n_fresh; ++c) {           // slots claimed by this step: wait until the epilogue has read them
-          const long long J = j0 + w.o_lo + w.n - w.n_fresh + c;
-          ptx::mbar_wait_timed(&ctrl->tmem_empty[J & (kWalkSlots - 1)], (uint32_t)(((J >> 3) & 1) ^ 1), p.err_flag, 2, &w_tmem);
-        }
-        ptx::mbar_wait_timed(&ctrl->a_full[aslot], aphase, p.err_flag, 3, &w_a);
         ptx::tc_fence_after();
         const uint32_t a_lo = a_base + aslot * (kSlabBytes >> 4);
         const uint64_t da0 = desc_hi | (uint64_t)a_lo;
         const uint64_t db0 = desc_hi | (uint64_t)b_base;
-        // one elected lane issues the whole step: K step 0 (tap 0, k = 0) apart, because fresh slots must not
-        // accumulate; the other 15 K steps are one MMA over the whole window, two where the slot ring wraps
-        if (ptx::elect_one()) {
-          walk_segments(w, true, [&](int slot, int bi, int nb, int fresh) {
-            ptx::umma_f16(tmem_base + (uint32_t)slot * 64, da0, db0 + (uint64_t)(bi * ((64 * 128) >> 4)),
-                          idesc0 | ((uint32_t)(nb * 64 >> 3) << 17), fresh ? 0u : 1u);
-          });
-          const uint32_t d_a = tmem_base + (uint32_t)w.slot0 * 64, d_b = tmem_base;
-          const uint32_t i_a = idesc0 | ((uint32_t)(w.n1 * 64 >> 3) << 17), i_b = idesc0 | ((uint32_t)((w.n - w.n1) * 64 >> 3) << 17);
-          const uint64_t db_a = db0 + (uint64_t)(w.bi0 * ((64 * 128) >> 4)), db_b = db_a + (uint64_t)(w.n1 * ((64 * 128) >> 4));
+        const uint32_t d_a = tmem_base + (uint32_t)w.slot0 * 64, d_b = tmem_base;
+        const uint32_t i_a = idesc0 | ((uint32_t)(w.n1 * 64 >> 3) << 17), i_b = idesc0 | ((uint32_t)((w.n - w.n1) * 64 >> 3) << 17);
+        const uint64_t db_a = db0 + (uint64_t)(w.bi0 * ((64 * 128) >> 4)), db_b = db_a + (uint64_t)(w.n1 * ((64 * 128) >> 4));
+        // K steps kk = 4 kw + k (tap kw = slab rows shifted by kw): one MMA over the whole window, two where the ring wraps
+        auto issue = [&](int kk_lo, int kk_hi) {
           if (w.n == w.n1) {
 #pragma unroll
-            for (int kk = 1; kk < kWalkKW * 4; ++kk) {
-              const int kw = kk >> 2, k = kk & 3;                                  // tap kw = slab rows shifted by kw
+            for (int kk = kk_lo; kk < kk_hi; ++kk) {
+              const int kw = kk >> 2, k = kk & 3;
               ptx::umma_f16(d_a, da0 + (uint64_t)(kw * 8 + 2 * k), db_a + (uint64_t)(kw * (kBTile >> 4) + 2 * k), i_a, 1u);
             }
           } else {
 #pragma unroll
-            for (int kk = 1; kk < kWalkKW * 4; ++kk) {
+            for (int kk = kk_lo; kk < kk_hi; ++kk) {
               const int kw = kk >> 2, k = kk & 3;
               const uint64_t da = da0 + (uint64_t)(kw * 8 + 2 * k);
               const uint64_t bo = (uint64_t)(kw * (kBTile >> 4) + 2 * k);
@@ -264,14 +264,29 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               ptx::umma_f16(d_b, da, db_b + bo, i_b, 1u);
             }
           }
+        };
+        // one elected lane issues the whole step: K step 0 apart, because fresh slots must not accumulate
+        if (ptx::elect_one()) {
+          walk_segments(w, true, [&](int slot, int bi, int nb, int fresh) {
+            ptx::umma_f16(tmem_base + (uint32_t)slot * 64, da0, db0 + (uint64_t)(bi * ((64 * 128) >> 4)),
+                          idesc0 | ((uint32_t)(nb * 64 >> 3) << 17), fresh ? 0u : 1u);
+          });
+          issue(1, 12);
         }
         __syncwarp();
+        // while those 12 MMAs are queued: the barrier waits of the NEXT step (an already-complete mbarrier.try_wait still
+        // costs ~90 cycles, and the tensor pipe's queue is too short to cover two of them plus the window arithmetic)
+        uint32_t nslot = aslot + 1, nphase = aphase;
+        if (nslot == (uint32_t)kNA) { nslot = 0; nphase ^= 1; }
+        if (r + 1 < H) wait_step(seq, r + 1, nslot, nphase);
+        else if (tile + (int)gridDim.x < num_tiles) wait_step(seq + 1, 0, nslot, nphase);
         if (ptx::elect_one()) {
+          issue(12, kWalkKW * 4);
           ptx::umma_commit(&ctrl->a_empty[aslot]);
           for (int d = 0; d < w.n_done; ++d) ptx::umma_commit(&ctrl->tmem_full[(j0 + w.done_lo + d) & (kWalkSlots - 1)]);
         }
         __syncwarp();
-        if (++aslot == (uint32_t)kNA) { aslot = 0; aphase ^= 1; }
+        aslot = nslot; aphase = nphase;
       }
     }
     if (p.debug_stats && lane == 0) {

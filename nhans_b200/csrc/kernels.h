@@ -55,6 +55,7 @@ struct GemmCfg {              // chosen by the host per layer shape
   int na, nb;                 // A slab ring / B tile ring depth
   int resident;               // all k-blocks of B fit in the ring: load once
   int desc_mode;              // 1: set the descriptor base-offset field for row-shifted slabs
+  int no_early;               // debug (NHANS_DESC_MODE bit 5): the issuer does not probe the next group's barriers early
   int il;                     // sub-tiles whose MMAs are interleaved (1, 2 or 4; divides mt, <= na)
   int tab_bytes;              // > 0: the fp16 time / frequency tables are staged in shared memory
   int cta2;                   // 1: CTA pairs (cta_group::2): M = 256 MMAs, each CTA loads half of B
