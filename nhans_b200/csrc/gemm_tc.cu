@@ -85,7 +85,7 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   const int MT = cfg.mt;
   const int num_groups = p.num_groups;
   // CTA pairs: M = 256 (bit 24.. holds M >> 4), issued by the leader for both CTAs
-  const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)p.BN) + (CTA2 ? (8u << 24) : 0u);
+  const uint32_t idesc = ptx::umma_idesc_f16((uint32_t)(cfg.dbg & 4 ? p.BN >> 1 : p.BN)) + (CTA2 ? (8u << 24) : 0u);
   const uint64_t desc_hi = ptx::umma_desc_sw128(0, 0);             // everything but the address field
   const uint32_t a_base = ptx::smem_u32(smem_a) >> 4, b_base = ptx::smem_u32(smem_b) >> 4;
   const uint32_t b_step = (uint32_t)b_bytes >> 4;
@@ -717,7 +717,9 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         uint64_t* gbar = &ctrl->a_full[slot];               // the group's slabs complete on its first slab's barrier
         for (int i = 0; i < MT; ++i) {
           ptx::mbar_wait(&ctrl->a_empty[slot], phase ^ 1, p.err_flag, 1);
-          if (ptx::elect_one()) {
+          if (cfg.dbg & 1) {
+            if (rank == 0 && i == 0 && ptx::elect_one()) ptx::mbar_arrive(gbar);
+          } else if (ptx::elect_one()) {
             if (CTA2) {
               // both CTAs' slabs are credited to the leader's barrier
               if (rank == 0 && i == 0) ptx::mbar_expect_tx(gbar, 2 * MT * kSlabBytes);
@@ -758,7 +760,9 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           for (int t = 0; t < ntaps; ++t) {
             const int bk = ctrl->groups[g].bk[t];
             ptx::mbar_wait(&ctrl->b_empty[slot], phase ^ 1, p.err_flag, 5);
-            if (ptx::elect_one()) {
+            if (cfg.dbg & 2) {
+              if (rank == 0 && t == 0 && ptx::elect_one()) ptx::mbar_arrive(gbar);
+            } else if (ptx::elect_one()) {
               if (CTA2) {
                 if (rank == 0 && t == 0) ptx::mbar_expect_tx(gbar, 2u * (uint32_t)(ntaps * b_bytes));
                 ptx::tma_load_2d_2sm(smem_b + (size_t)slot * b_bytes, &mapB, gbar, bk * 64, n0);
@@ -821,6 +825,7 @@ int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, int row, GemmCf
   c.resident = (num_kb <= c.nb && !cta2) ? 1 : 0;
   c.desc_mode = 0;
   c.no_early = 0;
+  c.dbg = 0;
   c.il = c.mt >= 2 ? 2 : 1;
   if (cfg) *cfg = c;
   return 1024 + c.na * kSlabBytes + c.nb * b_bytes + kCtrlBytes + epi_bytes + c.tab_bytes;
@@ -883,6 +888,7 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
   cfg.no_early = (desc_mode >> 5) & 1;
+  cfg.dbg = (desc_mode >> 6) & 7;
   if ((desc_mode >> 1) & 7) { cfg.il = (desc_mode >> 1) & 7; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
   if (cfg.nb < 4 || cfg.na % cfg.mt != 0) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight; its slabs never wrap the A ring
   const int tile_rows = (cfg.mt * 128) << cta2;
