@@ -195,10 +195,12 @@ stft_kernel(const int16_t* __restrict__ pcm, const float* __restrict__ xf, const
   const long long row0 = frame_offs[u] + t0 + warp * kFW;
   float* lm_w = logmag + (size_t)row0 * kBinsD;                       // 32-bit offsets from the warp's first row
   float* ph_w = phase ? phase + (size_t)row0 * kBinsD * (PHASOR ? 2 : 1) : nullptr;
+  float2 w_next = __ldg(&g_tw400[lane]);                              // table value of the next iteration: off the critical path
   for (int i = lane, f = 0, k = lane; i < nfw * 101; i += 32) {
     const float2 a = z[f * 200 + k];
     const float2 b = z[f * 200 + (k ? 200 - k : 0)];
-    const float2 w = __ldg(&g_tw400[k]);
+    const float2 w = w_next;
+    w_next = __ldg(&g_tw400[k + 32 >= 101 ? k + 32 - 101 : k + 32]);
     const float2 cb = cconj(b);
     const float2 E = cscale(cadd(a, cb), 0.5f), O = cscale(csub(a, cb), 0.5f);
     const float2 P = cmul(w, O);
@@ -233,36 +235,77 @@ __device__ __forceinline__ void istft_frames(float* __restrict__ s_y, const floa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* z = reinterpret_cast<float2*>(s_y) + warp * kFW * 200;
   const int t_first = fa + warp * kFW;
+  // The warp's four spectrum rows are contiguous in HBM (4 x 804 B of log-magnitudes, 4 x 1608 B of phasors): ask L2 for
+  // all of their lines first (no registers held), then read them in batches of kLB iterations with every load of a
+  // batch issued before the first use.  One element per iteration with the use right behind the load left the warp on
+  // a long-scoreboard stall for 44 % of its samples (ncu source page, round 2).
+  {
+    const int ta = max(t_first, 0), tb = min(t_first + kFW, T);
+    if (tb > ta) {
+      const char* l0 = reinterpret_cast<const char*>(logmag + (size_t)(row0 + ta) * kBinsD);
+      const char* p0 = reinterpret_cast<const char*>(phase + (size_t)(row0 + ta) * kBinsD * (PHASOR ? 2 : 1));
+      const int lbytes = (tb - ta) * kBinsD * 4, pbytes = lbytes * (PHASOR ? 2 : 1);
+      for (int o = lane * 128; o < lbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(l0 + o));
+      for (int o = lane * 128; o < pbytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+    }
+  }
   // S[k] = exp(logmag) * phasor; Z[k] = (S[k] + conj S[200-k]) + i e^{+2 pi i k / 400} (S[k] - conj S[200-k]) and
   // Z[200 - k] from the same pair
-  for (int i = lane, f = 0, k = lane; i < kFW * 101; i += 32) {
-    const int t = t_first + f;
-    float2 sk = make_float2(0.f, 0.f), sm = sk;
-    if (t >= 0 && t < T) {
-      const size_t o = (size_t)(row0 + t) * kBinsD;
-      // __expf: 2 ulp, i.e. ~1e-6 relative on |S| - far inside the 1e-5 absolute bound of the waveform tests
-      const float ak = __expf(logmag[o + k]), am = __expf(logmag[o + 200 - k]);
-      if (PHASOR) {
-        const float2 pk = reinterpret_cast<const float2*>(phase)[o + k], pm = reinterpret_cast<const float2*>(phase)[o + 200 - k];
-        sk = cscale(pk, ak);
-        sm = cscale(pm, am);
-      } else {
-        float sn, cs;
-        sincosf(phase[o + k], &sn, &cs);
-        sk = make_float2(ak * cs, ak * sn);
-        sincosf(phase[o + 200 - k], &sn, &cs);
-        sm = make_float2(am * cs, am * sn);
+  constexpr int kLoadIts = (kFW * 101 + 31) / 32, kLB = 4;
+#pragma unroll
+  for (int j0 = 0; j0 < kLoadIts; j0 += kLB) {
+    float lk[kLB], lm[kLB];
+    float2 pk[kLB], pm[kLB], w[kLB];
+    bool ok[kLB];
+#pragma unroll
+    for (int j = 0; j < kLB; ++j) {
+      const int i = lane + 32 * (j0 + j);
+      const int f = i / 101, k = i - 101 * f;
+      const int t = t_first + f;
+      ok[j] = j0 + j < kLoadIts && i < kFW * 101 && t >= 0 && t < T;
+      lk[j] = lm[j] = 0.f;
+      pk[j] = pm[j] = make_float2(0.f, 0.f);
+      if (ok[j]) {
+        const size_t o = (size_t)(row0 + t) * kBinsD;
+        lk[j] = logmag[o + k];
+        lm[j] = logmag[o + 200 - k];
+        if (PHASOR) {
+          pk[j] = reinterpret_cast<const float2*>(phase)[o + k];
+          pm[j] = reinterpret_cast<const float2*>(phase)[o + 200 - k];
+        } else {
+          pk[j].x = phase[o + k];
+          pm[j].x = phase[o + 200 - k];
+        }
       }
-      if (k == 0) { sk.y = 0.f; sm.y = 0.f; }           // irfft ignores the imaginary part of DC / Nyquist
+      w[j] = __ldg(&g_tw400[i < kFW * 101 ? k : 0]);     // conj(w) = e^{+2 pi i k / 400}
     }
-    const float2 w = __ldg(&g_tw400[k]);                 // conj(w) = e^{+2 pi i k / 400}
-    const float2 cm = cconj(sm);
-    const float2 e = cadd(sk, cm), d = csub(sk, cm);
-    const float2 wd = cmul(cconj(w), d);
-    z[f * 200 + k] = cadd(e, rot<true>(wd));                                  // e + i wd
-    if (k > 0 && k < 100) z[f * 200 + 200 - k] = cadd(cconj(e), make_float2(wd.y, wd.x));
-    k += 32;
-    if (k >= 101) { k -= 101; f += 1; }
+#pragma unroll
+    for (int j = 0; j < kLB; ++j) {
+      const int i = lane + 32 * (j0 + j);
+      if (j0 + j >= kLoadIts || i >= kFW * 101) continue;
+      const int f = i / 101, k = i - 101 * f;
+      float2 sk = make_float2(0.f, 0.f), sm = sk;
+      if (ok[j]) {
+        // __expf: 2 ulp, i.e. ~1e-6 relative on |S| - far inside the 1e-5 absolute bound of the waveform tests
+        const float ak = __expf(lk[j]), am = __expf(lm[j]);
+        if (PHASOR) {
+          sk = cscale(pk[j], ak);
+          sm = cscale(pm[j], am);
+        } else {
+          float sn, cs;
+          sincosf(pk[j].x, &sn, &cs);
+          sk = make_float2(ak * cs, ak * sn);
+          sincosf(pm[j].x, &sn, &cs);
+          sm = make_float2(am * cs, am * sn);
+        }
+        if (k == 0) { sk.y = 0.f; sm.y = 0.f; }           // irfft ignores the imaginary part of DC / Nyquist
+      }
+      const float2 cm = cconj(sm);
+      const float2 e = cadd(sk, cm), d = csub(sk, cm);
+      const float2 wd = cmul(cconj(w[j]), d);
+      z[f * 200 + k] = cadd(e, rot<true>(wd));                                  // e + i wd
+      if (k > 0 && k < 100) z[f * 200 + 200 - k] = cadd(cconj(e), make_float2(wd.y, wd.x));
+    }
   }
   __syncwarp();
   // pass A in place: task (f, m2) reads and writes the slots 25 j + m2
@@ -314,7 +357,7 @@ __device__ __forceinline__ int16_t to_i16(float v) { return (int16_t)__float2int
 // grid: (ceil((max_frames + 2) / kOH), U).  Output hop h (160 samples) sums frames h-2, h-1, h.  Clip lengths and
 // hop starts are multiples of 80 samples, so groups of four samples are aligned for 128-bit (f32) / 64-bit (int16) stores.
 template <bool PHASOR>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 istft_kernel(const float* __restrict__ logmag, const float* __restrict__ phase, const long long* __restrict__ frame_offs,
              const long long* __restrict__ out_offs, const int* __restrict__ peak, float* __restrict__ out_f32,
              int16_t* __restrict__ out_i16) {
