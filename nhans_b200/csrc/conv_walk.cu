@@ -234,11 +234,14 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
       ptx::mbar_wait_timed(&ctrl->a_full[slot], phase, p.err_flag, 3, &w_a);
     };
-    if ((int)blockIdx.x < num_tiles) wait_step(0, 0, 0, 0);
+    // (not with the generated operand: its slabs arrive just in time, and a wait in the middle of a step would hold back
+    // that step's last MMAs and commits - measured 1063 vs 1095 TFLOP/s on the same box)
+    if (!kGen && (int)blockIdx.x < num_tiles) wait_step(0, 0, 0, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
       const long long j0 = seq * H;
       for (int r = 0; r < H; ++r) {
         const WalkWin w = walk_window(seq, r, H, p.pt);
+        if (kGen) wait_step(seq, r, aslot, aphase);
         ptx::tc_fence_after();
         const uint32_t a_lo = a_base + aslot * (kSlabBytes >> 4);
         const uint64_t da0 = desc_hi | (uint64_t)a_lo;
@@ -278,8 +281,10 @@ conv64_walk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         // costs ~90 cycles, and the tensor pipe's queue is too short to cover two of them plus the window arithmetic)
         uint32_t nslot = aslot + 1, nphase = aphase;
         if (nslot == (uint32_t)kNA) { nslot = 0; nphase ^= 1; }
-        if (r + 1 < H) wait_step(seq, r + 1, nslot, nphase);
-        else if (tile + (int)gridDim.x < num_tiles) wait_step(seq + 1, 0, nslot, nphase);
+        if (!kGen) {
+          if (r + 1 < H) wait_step(seq, r + 1, nslot, nphase);
+          else if (tile + (int)gridDim.x < num_tiles) wait_step(seq + 1, 0, nslot, nphase);
+        }
         if (ptx::elect_one()) {
           issue(12, kWalkKW * 4);
           ptx::umma_commit(&ctrl->a_empty[aslot]);

@@ -96,7 +96,6 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
   if (ptx::elect_one()) {
     uint32_t aslot = 0, aphase = 0, bslot0 = 0, bphase0 = 0, it = 0;
     uint32_t full_par = 0;                                            // parity of b_full[s] as a group barrier, one bit per slot
-    bool pre_a = false, pre_b = false;                                // the current group's barrier waits were taken early
     bool b_ready = false;                                             // resident weights have landed
     long long w_tmem = 0, w_a = 0, w_b = 0;
     const long long t_start = clock64();
@@ -108,25 +107,8 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
       for (int g = g_lo; g < g_hi; ++g) {
         const int ntaps = ctrl->groups[g].ntaps;
         // the MT slabs of a group land on the barrier of the group's first slab (MT divides the ring depth, so a
-        // group never wraps), every B tile on the barrier of the group's first slot: two waits per group - and they
-        // are normally done while the previous group's last MMAs are still queued (`pre`, below)
-        if (!pre_a) ptx::mbar_wait_timed(&ctrl->a_full[aslot], aphase, p.err_flag, 3, &w_a);
-        if (!pre_b && !cfg.resident) {
-          ptx::mbar_wait_timed(&ctrl->b_full[bslot0], (full_par >> bslot0) & 1u, p.err_flag, 6, &w_b);
-          full_par ^= 1u << bslot0;
-        }
-        pre_a = pre_b = false;
-        // ring positions of the next group (this tile's next one, or the first one of this CTA's next tile).  Its
-        // operands can only be complete early if they do not need the slots this group still holds: the A ring must
-        // hold two groups, the B ring both groups' taps
-        uint32_t a_next = aslot + (uint32_t)MT, aph_next = aphase;
-        if (a_next >= (uint32_t)cfg.na) { a_next -= cfg.na; aph_next ^= 1; }
-        uint32_t b_next = bslot0 + (uint32_t)ntaps;
-        if (b_next >= (uint32_t)cfg.nb) b_next -= cfg.nb;
-        const int tile_next = tile + (int)(gridDim.x >> cta_shift);
-        const int g_next = g + 1 < g_hi ? g + 1 : (tile_next < num_tiles ? (tile_next % p.ksplit) * gper : -1);
-        const bool early_a = g_next >= 0 && !cfg.no_early && 2 * MT <= cfg.na;
-        const bool early_b = g_next >= 0 && !cfg.no_early && !cfg.resident && ntaps + ctrl->groups[g_next < 0 ? 0 : g_next].ntaps <= cfg.nb;
+        // group never wraps): one wait per group
+        ptx::mbar_wait_timed(&ctrl->a_full[aslot], aphase, p.err_flag, 3, &w_a);
         for (int i0 = 0; i0 < MT; i0 += IL) {
           uint32_t a_lo[IL], d_tm[IL];
 #pragma unroll
@@ -135,19 +117,12 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
             d_tm[ii] = tmem_base + acc * 256 + (i0 + ii) * p.BN;
           }
           uint32_t bslot = bslot0, bphase = bphase0;
+          if (i0 == 0 && !cfg.resident) {
+            // every B tile of the group lands on the barrier of the group's first slot: one wait per group
+            ptx::mbar_wait_timed(&ctrl->b_full[bslot0], (full_par >> bslot0) & 1u, p.err_flag, 6, &w_b);
+            full_par ^= 1u << bslot0;
+          }
           for (int t = 0; t < ntaps; ++t) {
-            if (i0 + IL >= MT && t == ntaps - 1) {
-              // the group's last MMAs are about to be issued and the ones before them are still queued: take the next
-              // group's barrier waits now (an already-complete mbarrier.try_wait costs ~90 cycles; at group boundaries
-              // two of them used to drain the tensor pipe's short queue)
-              // one probe each, never a blocking wait: operands that are still in flight are waited for at the top of
-              // the group, after this group's last MMAs and commits are queued
-              if (early_a) pre_a = ptx::mbar_test(&ctrl->a_full[a_next], aph_next);
-              if (early_b && ptx::mbar_test(&ctrl->b_full[b_next], (full_par >> b_next) & 1u)) {
-                full_par ^= 1u << b_next;
-                pre_b = true;
-              }
-            }
             if (cfg.resident) {
               bslot = (uint32_t)ctrl->groups[g].bk[t];
               if (!b_ready) ptx::mbar_wait_timed(&ctrl->b_full[bslot], 0u, p.err_flag, 6, &w_b);
@@ -887,7 +862,6 @@ cudaError_t launch_gemm(cudaStream_t s, int n_sm, const CUtensorMap& mapA0, cons
   const CUtensorMap& mapB = cta2 ? mapB_half : mapB_full;
   if (p.N != p.BN) cfg.resident = 0;
   cfg.desc_mode = desc_mode & 1;
-  cfg.no_early = (desc_mode >> 5) & 1;
   cfg.dbg = (desc_mode >> 6) & 7;
   if ((desc_mode >> 1) & 7) { cfg.il = (desc_mode >> 1) & 7; if (cfg.il > cfg.mt) cfg.il = cfg.mt; }   // debug override
   if (cfg.nb < 4 || cfg.na % cfg.mt != 0) return cudaErrorInvalidValue;   // a group has up to 4 taps in flight; its slabs never wrap the A ring

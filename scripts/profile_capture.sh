@@ -12,6 +12,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --c
 # 14 tower launches (Silent.wav embedding + the batch's contexts) and the first mask-network pass are skipped
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_shift|conv64_walk' -s 31 -c 17 -f -o /tmp/${TAG}_tc $B > $OUT/${TAG}_tc.log 2>&1
 ncu -i /tmp/${TAG}_tc.ncu-rep --page raw --csv > $OUT/${TAG}_tc_raw.csv 2>> $OUT/${TAG}_tc.log
+if [ -z "${SKIP_DSP_NCU:-}" ]; then
 timeout 600 ncu --set full --clock-control none -k regex:'stft_kernel|istft_kernel' -c 8 -f -o /tmp/${TAG}_dsp python bench.py --steps 1 --warmup 1 --utts 256 --no-cpu-baseline > $OUT/${TAG}_dsp.log 2>&1
 ncu -i /tmp/${TAG}_dsp.ncu-rep --page raw --csv > $OUT/${TAG}_dsp_raw.csv 2>> $OUT/${TAG}_dsp.log
+fi
 ls -la $OUT | grep ${TAG}
