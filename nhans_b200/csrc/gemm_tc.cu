@@ -203,7 +203,6 @@ __device__ __forceinline__ void epilogue_warp(Ctrl* ctrl, const GemmDev& p, cons
   };
   uint32_t it = 0;
   long long w_full = 0;
-#pragma unroll 1
   const int cta_shift = CTA2 ? 1 : 0;   // CTA pairs: a sub-tile is 256 rows, this CTA owns rows [128 rank, +128)
   const int sub_rows = 128 << cta_shift;
   auto release_acc = [&](uint32_t acc) {      // one arrival per warp on the (leader's) accumulator-free barrier
@@ -799,7 +798,6 @@ int gemm_smem_bytes(int BN, int num_kb, int tab_bytes, int cta2, int row, GemmCf
   if (c.nb > kMaxB) c.nb = kMaxB;
   c.resident = (num_kb <= c.nb && !cta2) ? 1 : 0;
   c.desc_mode = 0;
-  c.no_early = 0;
   c.dbg = 0;
   c.il = c.mt >= 2 ? 2 : 1;
   if (cfg) *cfg = c;

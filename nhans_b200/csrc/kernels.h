@@ -55,7 +55,6 @@ struct GemmCfg {              // chosen by the host per layer shape
   int na, nb;                 // A slab ring / B tile ring depth
   int resident;               // all k-blocks of B fit in the ring: load once
   int desc_mode;              // 1: set the descriptor base-offset field for row-shifted slabs
-  int no_early;               // debug (NHANS_DESC_MODE bit 5): the issuer does not probe the next group's barriers early
   int dbg;                    // timing experiments, results are garbage (NHANS_DESC_MODE bits 6-8): 1 no A loads, 2 no B loads, 4 MMAs of half the N
   int il;                     // sub-tiles whose MMAs are interleaved (1, 2 or 4; divides mt, <= na)
   int tab_bytes;              // > 0: the fp16 time / frequency tables are staged in shared memory
