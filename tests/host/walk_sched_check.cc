@@ -2,7 +2,8 @@
 // steps against a software model of the TMEM slot ring and checks that every output row receives exactly
 // the (input row, kernel row) products of a 'SAME'-style convolution with `pt` rows of top padding, that a
 // freshly claimed slot never accumulates, that the ring never wraps inside one MMA, and that the claim /
-// publish order cannot deadlock against an in-order epilogue.
+// publish order cannot deadlock against an in-order epilogue - also when, as in the kernel's issuer, the claims of
+// step s + 1 are waited for BEFORE the jobs that finish in step s are published.
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -26,6 +27,7 @@ using namespace nhans;
 struct Slot {
   long long job = -1;
   bool published = true;      // nothing to drain yet
+  long long pub_step = -100;  // global step whose commit published the slot's last job
   std::set<std::pair<int, int>> terms;     // (input row, kernel row)
 };
 
@@ -67,6 +69,7 @@ int main() {
       std::vector<Slot>& ring = M.ring;
       M.H = H; M.pt = pt;
       long long published_upto = -1;          // the epilogue drains jobs in order
+      long long gstep = 0;                    // steps since the start of the launch
       for (long long seq = 0; seq < 9; ++seq) {
         for (int r = 0; r < H; ++r) {
           M.seq = seq; M.r = r;
@@ -79,6 +82,9 @@ int main() {
             // published by an EARLIER step, otherwise the kernel deadlocks
             CHECK(s.published, "claim of job %lld: slot still owned by unpublished job %lld", J, s.job);
             CHECK(s.job < 0 || s.job == J - kWalkSlots, "slot reuse out of order");
+            // conv_walk.cu takes this wait in the middle of the PREVIOUS step, ahead of that step's tmem_full commits: the
+            // slot's last job must have been published by a step before that one
+            CHECK(s.pub_step <= gstep - 2, "early claim of job %lld: slot published only in step %lld (now %lld)", J, s.pub_step, gstep);
             s.job = J;
             s.published = false;
             s.terms.clear();
@@ -108,8 +114,10 @@ int main() {
             CHECK(J == published_upto + 1, "jobs published out of order (%lld after %lld)", J, published_upto);
             published_upto = J;
             s.published = true;
+            s.pub_step = gstep;
           }
           ++steps;
+          ++gstep;
           mmas_first += n_first;
           mmas_rest += n_rest;
         }
