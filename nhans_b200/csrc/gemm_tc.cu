@@ -78,7 +78,9 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // MMA issuer (one warp): walks tiles / groups / sub-tiles in the producers' order; one elected lane issues
 // tcgen05.mma.  IL sub-tiles are processed together so that consecutive MMAs target different TMEM
 // accumulators (back-to-back MMAs into the same accumulator serialise on the accumulate dependency).
-template <int IL, bool CTA2>
+// RES: the whole weight matrix is resident in the B ring (towers, small layers); compile-time because every runtime
+// test in the single issuing lane's tap loop is paid in throughput (the lane is instruction bound).
+template <int IL, bool CTA2, bool RES>
 __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const GemmCfg& cfg, uint8_t* smem_a, uint8_t* smem_b,
                                            uint32_t tmem_base, int num_tiles, int b_bytes) {
   const int cta_shift = CTA2 ? 1 : 0;
@@ -98,17 +100,22 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
     uint32_t full_par = 0;                                            // parity of b_full[s] as a group barrier, one bit per slot
     bool b_ready = false;                                             // resident weights have landed
     long long w_tmem = 0, w_a = 0, w_b = 0;
+    const bool stats = p.debug_stats != nullptr;                      // wait cycles are only clocked when somebody reads them
+    auto wait = [&](uint64_t* bar, uint32_t parity, int tag, long long* acc) {
+      if (stats) ptx::mbar_wait_timed(bar, parity, p.err_flag, tag, acc);
+      else ptx::mbar_wait(bar, parity, p.err_flag, tag);
+    };
     const long long t_start = clock64();
     for (int tile = blockIdx.x >> cta_shift; tile < num_tiles; tile += gridDim.x >> cta_shift, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int g_lo = (tile % p.ksplit) * gper, g_hi = min(num_groups, g_lo + gper);
-      ptx::mbar_wait_timed(&ctrl->tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2, &w_tmem);
+      wait(&ctrl->tmem_empty[acc], acc_phase ^ 1, 2, &w_tmem);
       ptx::tc_fence_after();
       for (int g = g_lo; g < g_hi; ++g) {
         const int ntaps = ctrl->groups[g].ntaps;
         // the MT slabs of a group land on the barrier of the group's first slab (MT divides the ring depth, so a
         // group never wraps): one wait per group
-        ptx::mbar_wait_timed(&ctrl->a_full[aslot], aphase, p.err_flag, 3, &w_a);
+        wait(&ctrl->a_full[aslot], aphase, 3, &w_a);
         for (int i0 = 0; i0 < MT; i0 += IL) {
           uint32_t a_lo[IL], d_tm[IL];
 #pragma unroll
@@ -117,15 +124,15 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
             d_tm[ii] = tmem_base + acc * 256 + (i0 + ii) * p.BN;
           }
           uint32_t bslot = bslot0, bphase = bphase0;
-          if (i0 == 0 && !cfg.resident) {
+          if (i0 == 0 && !RES) {
             // every B tile of the group lands on the barrier of the group's first slot: one wait per group
-            ptx::mbar_wait_timed(&ctrl->b_full[bslot0], (full_par >> bslot0) & 1u, p.err_flag, 6, &w_b);
+            wait(&ctrl->b_full[bslot0], (full_par >> bslot0) & 1u, 6, &w_b);
             full_par ^= 1u << bslot0;
           }
           for (int t = 0; t < ntaps; ++t) {
-            if (cfg.resident) {
+            if (RES) {
               bslot = (uint32_t)ctrl->groups[g].bk[t];
-              if (!b_ready) ptx::mbar_wait_timed(&ctrl->b_full[bslot], 0u, p.err_flag, 6, &w_b);
+              if (!b_ready) wait(&ctrl->b_full[bslot], 0u, 6, &w_b);
             }
             ptx::tc_fence_after();
             const uint32_t sh = (uint32_t)ctrl->groups[g].shift[t] * 8;
@@ -140,10 +147,10 @@ __device__ __forceinline__ void mma_issuer(Ctrl* ctrl, const GemmDev& p, const G
                 else ptx::umma_f16(d_tm[ii], (desc_hi | (a_lo[ii] + sh)) + 2 * k, db + 2 * k, idesc, k == 0 ? first : 1u);
               }
             }
-            if (i0 + IL >= MT && !cfg.resident) {
+            if (i0 + IL >= MT && !RES) {
               if (CTA2) ptx::umma_commit_2sm(&ctrl->b_empty[bslot]); else ptx::umma_commit(&ctrl->b_empty[bslot]);
             }
-            if (!cfg.resident && ++bslot == (uint32_t)cfg.nb) { bslot = 0; bphase ^= 1; }
+            if (!RES && ++bslot == (uint32_t)cfg.nb) { bslot = 0; bphase ^= 1; }
           }
 #pragma unroll
           for (int ii = 0; ii < IL; ++ii) {
@@ -755,9 +762,15 @@ gemm_shift_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // ===================== MMA issuer =====================
     if (rank != 0) {
       // the peer CTA of a pair only lends its shared memory / TMEM; the leader issues for both
-    } else if (cfg.il == 4) mma_issuer<4, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
-    else if (cfg.il == 2) mma_issuer<2, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
-    else mma_issuer<1, CTA2>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+    } else if (cfg.resident) {
+      if (cfg.il == 4) mma_issuer<4, CTA2, true>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+      else if (cfg.il == 2) mma_issuer<2, CTA2, true>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+      else mma_issuer<1, CTA2, true>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+    } else {
+      if (cfg.il == 4) mma_issuer<4, CTA2, false>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+      else if (cfg.il == 2) mma_issuer<2, CTA2, false>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+      else mma_issuer<1, CTA2, false>(ctrl, p, cfg, smem_a, smem_b, tmem_base, num_tiles, b_bytes);
+    }
   } else {
     // ===================== epilogue (warps 0..7) =====================
     if (kRow) epilogue_warp_row<EPI, CTA2>(ctrl, p, cfg, warp - kEpiWarp0, lane, tmem_base, num_tiles, n_tiles, s_ttab, s_ftab, s_rs, s_r1, rank);
